@@ -1,0 +1,167 @@
+/*
+ * starvector_b200 — C-ABI of the B200-native im2svg generation engine.
+ *
+ * The reference (joanrod/star-vector) has no FFI: its boundary for this path is the Python
+ * method surface `StarVectorForCausalLM.generate_im2svg` / `.model.svg_transformer
+ * .transformer.generate` (reference: starvector/model/starvector_arch.py:186-187,
+ * starvector/model/models/starvector_base.py:203-259).  The Python facade in
+ * `starvector_b200/modeling.py` keeps that surface and binds THESE entry points with ctypes
+ * (see INTEGRATION.md).  Each entry point below names the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE
+ * pointer unless the name ends in `_host` or the comment says "host or device"; `stream` is
+ * a `cudaStream_t` passed as `void*` (NULL = legacy default stream); return 0 on success,
+ * <0 on error with the message available from `sv_last_error`; no exceptions cross the
+ * ABI; an engine is not re-entrant (the caller serialises; the Python shim holds a lock).
+ * There is no CPU fallback: every call fails with SV_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef STARVECTOR_B200_H
+#define STARVECTOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SV_ABI_VERSION 1
+#if defined(__GNUC__)
+#define SV_API __attribute__((visibility("default")))
+#else
+#define SV_API
+#endif
+
+enum {
+  SV_OK = 0,
+  SV_ERR_INVALID = -1,     /* bad argument / shape / name */
+  SV_ERR_CUDA = -2,        /* CUDA runtime or driver error (message has the cudaError string) */
+  SV_ERR_UNSUPPORTED = -3, /* valid request this build does not implement (e.g. variant 1 = 8B) */
+  SV_ERR_STATE = -4        /* call order violated (weights missing, no prefill before generate, ...) */
+};
+
+enum { SV_DTYPE_BF16 = 0, SV_DTYPE_F32 = 1, SV_DTYPE_F16 = 2 };
+
+/* activation selectors of the fused linear epilogue */
+enum {
+  SV_ACT_NONE = 0,
+  SV_ACT_QUICKGELU = 1, /* x*sigmoid(1.702x)  — clip_model.py:126-128 */
+  SV_ACT_GELU_TANH = 2, /* gelu_pytorch_tanh  — GPTBigCodeMLP */
+  SV_ACT_SILU = 3       /* x*sigmoid(x)       — adapters/adapter.py:5-10 */
+};
+
+/* implementation selector for sv_op_linear (tests cross-check the two kernels) */
+enum { SV_LINEAR_AUTO = 0, SV_LINEAR_ROWGROUP = 1, SV_LINEAR_TCGEN05 = 2 };
+
+typedef struct sv_engine sv_engine;
+
+/* Dimensions of one StarVector model (reference: image_encoder.py:50-61,
+ * starvector_base.py:87-104, adapters/adapter.py:13-31, bigcode/starcoderbase-1b config). */
+typedef struct sv_model_desc {
+  int32_t variant;      /* 0 = v1: CLIP ViT + Adapter + GPTBigCode (MQA).  1 = v2 (8B): unsupported */
+  int32_t image_size;   /* 224 */
+  int32_t patch_size;   /* 14  */
+  int32_t vit_width;    /* 1024 */
+  int32_t vit_layers;   /* 23 (penultimate-layer CLIP ViT-L/14) */
+  int32_t vit_heads;    /* 16 (head dim must be 64) */
+  int32_t vit_mlp;      /* 4096 */
+  int32_t adapter_norm; /* 0 = LayerNorm([Q,H]); 1 = BatchNorm1d(Q) in eval mode */
+  int32_t hidden;       /* 2048 */
+  int32_t n_layer;      /* 24 */
+  int32_t n_head;       /* 16 */
+  int32_t n_kv_head;    /* 1 (multi-query) */
+  int32_t head_dim;     /* 128 */
+  int32_t n_inner;      /* 8192 */
+  int32_t n_positions;  /* 8192 learned absolute positions */
+  int32_t vocab;        /* 49156 = 49152 + [PAD] + 3 added tokens (llm/starcoder.py:43-53) */
+  float ln_eps;         /* 1e-5 */
+  int32_t max_batch;    /* images per call on this GPU */
+  int32_t max_len;      /* KV-cache capacity in tokens (prefix + generated) */
+} sv_model_desc;
+
+/* Decoding parameters = the kwargs the reference forwards to HF generate()
+ * (starvector_base.py:223-241, :289-295) after HF's own length fix-up. */
+typedef struct sv_gen_params {
+  int32_t max_new_tokens;    /* = max_length - (Q + P)  (generation/utils.py:1629-1638) */
+  int32_t do_sample;         /* use_nucleus_sampling; 0 = greedy argmax (lowest index wins ties) */
+  float temperature;
+  float top_p;
+  float repetition_penalty;  /* applies to generated ids only (App. B.4) */
+  int32_t eos_token_id;      /* -1 = none (throughput configs) */
+  int32_t pad_token_id;
+  int32_t n_stop_ids;        /* 0..8: ids of '</svg>' (StoppingCriteriaSub, starvector_base.py:9-20) */
+  int32_t stop_ids[8];
+  int32_t stop_row0_only;    /* 1 = reference behaviour D6 (row 0 matching ends the WHOLE batch);
+                                0 = per-row: a matching row is finished/padded, batch ends when all rows are */
+  uint64_t seed;             /* Philox seed for sampling */
+  int32_t poll_interval;     /* host polls the device stop flag every this many steps (0 -> 16) */
+} sv_gen_params;
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+SV_API int sv_abi_version(void);
+/* Replaces module construction (starvector_base.py:22-48): allocates packed weights, KV cache
+ * and workspaces on `device`. */
+SV_API int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out);
+SV_API void sv_engine_destroy(sv_engine* e);
+/* Message for the last failing call on `e` (or the last failing create when e == NULL). */
+SV_API const char* sv_last_error(const sv_engine* e);
+/* Replaces load_state_dict/from_pretrained: copy one tensor by its reference state-dict name
+ * (SURVEY.md §8b "Ownership"), e.g. "model.image_encoder.visual_encoder.conv1.weight".
+ * `data` may be a host or device pointer (UVA); borrowed only during the call. */
+SV_API int sv_engine_load_weight(sv_engine* e, const char* hf_name, const void* data, const int64_t* shape,
+                          int32_t ndim, int32_t dtype);
+/* Number of tensors still missing (0 = ready); names (newline separated) via sv_last_error. */
+SV_API int sv_engine_missing_weights(sv_engine* e);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* ImageEncoder.forward + Adapter.forward (image_encoder.py:91-94, adapter.py:33-39,
+ * starvector_base.py:206-209).  pixels: bf16 [B,3,S,S].  Result stays resident as the visual
+ * prefix; if out_embeds != NULL it is also copied there (bf16 [B,Q,H]).  If vit_out != NULL the
+ * pre-adapter `ln_vision` output (bf16 [B,Q,W]) is copied there (parity tests). */
+SV_API int sv_encode_images(sv_engine* e, const void* pixels, int32_t batch, void* out_embeds, void* vit_out,
+                     void* stream);
+/* Prompt embedding + concat (starvector_base.py:213-219) and the decoder prefill over the
+ * Q+P prefix (the first forward inside generate()).  prompt_ids int32 [B,P].
+ * last_logits (optional) float [B,V]: logits of the last prefix position. */
+SV_API int sv_prefill(sv_engine* e, const int32_t* prompt_ids, int32_t batch, int32_t prompt_len,
+               float* last_logits, void* stream);
+/* The same prefill from caller-provided inputs_embeds bf16 [B,T,H] (the `.generate(inputs_embeds=...)`
+ * form of starvector_base.py:255; wpe is added inside, as GPTBigCodeModel.forward does). */
+SV_API int sv_prefill_embeds(sv_engine* e, const void* inputs_embeds, int32_t batch, int32_t seq_len,
+                             float* last_logits, void* stream);
+/* One teacher-forced decode step: feed ids int32 [B], append to the KV cache, return fp32 logits
+ * [B,V] (optional).  The parity-test hook; also the body the generate loop replays. */
+SV_API int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream);
+/* GenerationMixin.generate() after the prefill (greedy / sampling loop, App. B): runs up to
+ * max_new_tokens steps as a replayed CUDA graph.  out_ids int32 [B,max_new_tokens] (new tokens
+ * only, padded with pad_token_id), out_len int32 [B] = rectangular generated length.
+ * Synchronises `stream` before returning. */
+SV_API int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t* out_len, void* stream);
+/* Whole path with HOST buffers (copies inside): pixels_host bf16 [B,3,S,S], prompt_ids_host
+ * int32 [B,P] -> out_ids_host int32 [B,max_new_tokens], out_len_host int32 [B]. */
+SV_API int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_t batch,
+                            const int32_t* prompt_ids_host, int32_t prompt_len, const sv_gen_params* p,
+                            int32_t* out_ids_host, int32_t* out_len_host, void* stream);
+
+/* ---- introspection for bench/profiles ------------------------------------------------- */
+/* Kernel launches issued by this engine since creation (graph replays count their nodes). */
+SV_API int64_t sv_launch_count(const sv_engine* e);
+/* Device time (ms) of the last sv_generate decode loop and its step count, from CUDA events
+ * recorded on the launching stream. */
+SV_API int sv_last_decode_timing(const sv_engine* e, float* ms, int32_t* steps);
+
+/* ---- single-kernel entry points (unit parity tests; all bf16 unless noted) -------------- */
+SV_API int sv_op_layernorm(const void* x, const void* w, const void* b, void* y, int32_t rows, int32_t cols,
+                    float eps, void* stream);
+/* y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]) (+ residual[M,N]); rounding points follow the
+ * reference's bf16 module boundaries. */
+SV_API int sv_op_linear(int32_t impl, const void* x, const void* w, const void* bias, const void* residual, void* y,
+                 int32_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* ViT self-attention over packed qkv [B*L, 3*heads*64] -> out [B*L, heads*64]. */
+SV_API int sv_op_attention_vit(const void* qkv, void* out, int32_t batch, int32_t seq, int32_t heads, void* stream);
+/* Causal multi-query attention over packed qkv [B*T, heads*D + 2*D] (D=128) -> out [B*T, heads*D]. */
+SV_API int sv_op_attention_mqa(const void* qkv, void* out, int32_t batch, int32_t seq, int32_t heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARVECTOR_B200_H */

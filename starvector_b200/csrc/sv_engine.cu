@@ -1,0 +1,756 @@
+// C-ABI of the im2svg engine (include/starvector_b200.h): engine state, weight registry, the
+// encode -> prefill -> decode orchestration and the CUDA-graph generation loop.
+//
+// Reference path being replaced: StarVectorBase.generate_im2svg
+// (starvector/model/models/starvector_base.py:203-259) = ImageEncoder (image_encoder.py:91-94,
+// clip_model.py:181-191) -> Adapter (adapters/adapter.py:33-39) -> prompt concat -> HF
+// GenerationMixin.generate over GPTBigCodeForCausalLM.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/starvector_b200.h"
+#include "sv_kernels.h"
+
+using namespace sv;
+
+namespace {
+
+constexpr int kMaxPrompt = 64;
+constexpr int kMaxSplit = 128;
+
+std::string g_create_error;
+
+struct Weight {
+  bf16* p = nullptr;
+  std::vector<int64_t> shape;      // shape expected from the caller (reference layout)
+  int64_t numel = 0;
+  bool loaded = false;
+  bool optional = false;
+};
+
+struct VitLayer { bf16 *ln1_w, *ln1_b, *qkv_w, *qkv_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *proj_w, *proj_b; };
+struct DecLayer { bf16 *ln1_w, *ln1_b, *attn_w, *attn_b, *proj_w, *proj_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *fc2_w, *fc2_b; };
+
+struct GraphEntry { cudaGraphExec_t exec = nullptr; int kernels = 0; };
+
+}  // namespace
+
+struct sv_engine {
+  sv_model_desc d{};
+  int device = 0;
+  std::string err;
+  int64_t launches = 0;
+  int linear_impl = SV_LINEAR_AUTO;
+
+  int Q = 0, NP = 0, Kp = 0, Lpad = 0, qkv_cols = 0, tcap = 0;
+  std::map<std::string, Weight> w;
+  std::vector<void*> allocs;
+
+  // resolved weights
+  bf16 *conv_w = nullptr, *conv_raw = nullptr, *cls = nullptr, *pos = nullptr, *lnpre_w = nullptr, *lnpre_b = nullptr;
+  bf16 *lnv_w = nullptr, *lnv_b = nullptr;
+  std::vector<VitLayer> vit;
+  bf16 *afc_w = nullptr, *afc_b = nullptr, *aproj_w = nullptr, *aproj_b = nullptr, *anorm_w = nullptr, *anorm_b = nullptr,
+       *anorm_rm = nullptr, *anorm_rv = nullptr;
+  bf16 *wte = nullptr, *wpe = nullptr, *lnf_w = nullptr, *lnf_b = nullptr, *lm_head = nullptr;
+  std::vector<DecLayer> dec;
+
+  // activations / workspaces
+  bf16 *v_patches, *v_pe, *v_x, *v_ln, *v_qkv, *v_vt, *v_attn, *v_h, *v_out, *a_h, *a_z, *visual;
+  float* slab_partial;
+  bf16 *p_x, *p_ln, *p_qkv, *p_attn, *p_h;
+  bf16 *d_x, *d_ln, *d_qkv, *d_attn, *d_h, *d_last, *logits;
+  float *logits_f32, *attn_partial;
+  bf16 *kcache, *vtcache;           // [layer][max_batch][n_kv][tcap][D] / [layer][max_batch][n_kv][D][tcap]
+  int64_t cache_layer_stride = 0;
+  GenState* state = nullptr;
+  GenParamsDev* params = nullptr;
+  uint8_t* seen = nullptr;
+  int32_t *next_ids = nullptr, *out_ids = nullptr, *ids_tmp = nullptr;
+  int32_t* host_flag = nullptr;     // pinned
+
+  // run state (host mirror)
+  int cur_batch = 0, prefix_len = 0, host_cur_len = 0;
+  bool encoded = false, prefilled = false;
+
+  cudaStream_t gen_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  std::map<long long, GraphEntry> graphs;   // key = batch * 1000 + nsplit * 2 + do_sample
+  float last_decode_ms = 0.f;
+  int last_decode_steps = 0;
+};
+
+namespace {
+
+int fail(sv_engine* e, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define SV_CK(e, call)                                                                              \
+  do {                                                                                              \
+    cudaError_t _err = (call);                                                                      \
+    if (_err != cudaSuccess)                                                                        \
+      return fail((e), SV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_err), __FILE__, __LINE__); \
+  } while (0)
+
+struct LaunchScope {   // routes count_launch() of this thread to the engine's counter
+  explicit LaunchScope(sv_engine* e) { g_launch_counter = &e->launches; }
+  ~LaunchScope() { g_launch_counter = nullptr; }
+};
+
+template <typename T>
+cudaError_t dev_alloc(sv_engine* e, T** p, int64_t n) {
+  void* q = nullptr;
+  cudaError_t r = cudaMalloc(&q, (size_t)std::max<int64_t>(n, 1) * sizeof(T));
+  if (r == cudaSuccess) { e->allocs.push_back(q); *p = reinterpret_cast<T*>(q); }
+  return r;
+}
+
+bf16* add_weight(sv_engine* e, const std::string& name, std::vector<int64_t> shape, int64_t alloc_numel = -1,
+                 bool optional = false) {
+  Weight wt;
+  wt.shape = shape;
+  wt.numel = 1;
+  for (auto s : shape) wt.numel *= s;
+  wt.optional = optional;
+  int64_t n = alloc_numel > 0 ? alloc_numel : wt.numel;
+  if (dev_alloc(e, &wt.p, n) != cudaSuccess) return nullptr;
+  cudaMemset(wt.p, 0, (size_t)n * sizeof(bf16));
+  bf16* p = wt.p;
+  e->w[name] = std::move(wt);
+  return p;
+}
+
+const char* VIS = "model.image_encoder.visual_encoder.";
+const char* LNV = "model.image_encoder.ln_vision.";
+const char* ADP = "model.image_projection.";
+const char* DEC = "model.svg_transformer.transformer.transformer.";
+const char* LMH = "model.svg_transformer.transformer.lm_head.weight";
+
+bool build_weights(sv_engine* e) {
+  const sv_model_desc& d = e->d;
+  const int64_t W = d.vit_width, Q = e->Q, H = d.hidden, kv = (int64_t)d.n_kv_head * d.head_dim, I = d.n_inner;
+  bool ok = true;
+  auto A = [&](const std::string& n, std::vector<int64_t> s, int64_t alloc = -1, bool opt = false) {
+    bf16* p = add_weight(e, n, std::move(s), alloc, opt);
+    ok = ok && p != nullptr;
+    return p;
+  };
+  std::string v = VIS;
+  e->conv_raw = A(v + "conv1.weight", {W, 3, d.patch_size, d.patch_size});
+  ok = ok && dev_alloc(e, &e->conv_w, W * e->Kp) == cudaSuccess;
+  e->cls = A(v + "class_embedding", {W});
+  e->pos = A(v + "positional_embedding", {Q, W});
+  e->lnpre_w = A(v + "ln_pre.weight", {W});
+  e->lnpre_b = A(v + "ln_pre.bias", {W});
+  e->vit.resize(d.vit_layers);
+  for (int i = 0; i < d.vit_layers; ++i) {
+    std::string p = v + "transformer.resblocks." + std::to_string(i) + ".";
+    VitLayer& L = e->vit[i];
+    L.ln1_w = A(p + "ln_1.weight", {W}); L.ln1_b = A(p + "ln_1.bias", {W});
+    L.qkv_w = A(p + "attn.in_proj_weight", {3 * W, W}); L.qkv_b = A(p + "attn.in_proj_bias", {3 * W});
+    L.out_w = A(p + "attn.out_proj.weight", {W, W}); L.out_b = A(p + "attn.out_proj.bias", {W});
+    L.ln2_w = A(p + "ln_2.weight", {W}); L.ln2_b = A(p + "ln_2.bias", {W});
+    L.fc_w = A(p + "mlp.c_fc.weight", {(int64_t)d.vit_mlp, W}); L.fc_b = A(p + "mlp.c_fc.bias", {(int64_t)d.vit_mlp});
+    L.proj_w = A(p + "mlp.c_proj.weight", {W, (int64_t)d.vit_mlp}); L.proj_b = A(p + "mlp.c_proj.bias", {W});
+  }
+  e->lnv_w = A(std::string(LNV) + "weight", {W});
+  e->lnv_b = A(std::string(LNV) + "bias", {W});
+  std::string a = ADP;
+  e->afc_w = A(a + "c_fc.weight", {2 * W, W}); e->afc_b = A(a + "c_fc.bias", {2 * W});
+  e->aproj_w = A(a + "c_proj.weight", {H, 2 * W}); e->aproj_b = A(a + "c_proj.bias", {H});
+  if (d.adapter_norm == 0) {
+    e->anorm_w = A(a + "norm.weight", {Q, H}); e->anorm_b = A(a + "norm.bias", {Q, H});
+  } else {
+    e->anorm_w = A(a + "norm.weight", {Q}); e->anorm_b = A(a + "norm.bias", {Q});
+    e->anorm_rm = A(a + "norm.running_mean", {Q}); e->anorm_rv = A(a + "norm.running_var", {Q});
+  }
+  std::string t = DEC;
+  e->wte = A(t + "wte.weight", {(int64_t)d.vocab, H});
+  e->wpe = A(t + "wpe.weight", {(int64_t)d.n_positions, H});
+  e->dec.resize(d.n_layer);
+  for (int i = 0; i < d.n_layer; ++i) {
+    std::string p = t + "h." + std::to_string(i) + ".";
+    DecLayer& L = e->dec[i];
+    L.ln1_w = A(p + "ln_1.weight", {H}); L.ln1_b = A(p + "ln_1.bias", {H});
+    L.attn_w = A(p + "attn.c_attn.weight", {H + 2 * kv, H}); L.attn_b = A(p + "attn.c_attn.bias", {H + 2 * kv});
+    L.proj_w = A(p + "attn.c_proj.weight", {H, H}); L.proj_b = A(p + "attn.c_proj.bias", {H});
+    L.ln2_w = A(p + "ln_2.weight", {H}); L.ln2_b = A(p + "ln_2.bias", {H});
+    L.fc_w = A(p + "mlp.c_fc.weight", {I, H}); L.fc_b = A(p + "mlp.c_fc.bias", {I});
+    L.fc2_w = A(p + "mlp.c_proj.weight", {H, I}); L.fc2_b = A(p + "mlp.c_proj.bias", {H});
+  }
+  e->lnf_w = A(t + "ln_f.weight", {H});
+  e->lnf_b = A(t + "ln_f.bias", {H});
+  e->lm_head = e->wte;   // tied (train/util.py:68-77); an explicit lm_head.weight un-ties it
+  return ok;
+}
+
+bool build_buffers(sv_engine* e) {
+  const sv_model_desc& d = e->d;
+  const int64_t B = d.max_batch, W = d.vit_width, H = d.hidden, I = d.n_inner, D = d.head_dim;
+  const int64_t Mv = B * e->Q, Mp = B * (e->Q + kMaxPrompt), heads = d.vit_heads;
+  bool ok = true;
+#define AL(ptr, n) ok = ok && (dev_alloc(e, &e->ptr, (n)) == cudaSuccess)
+  AL(v_patches, B * e->NP * e->Kp); AL(v_pe, B * e->NP * W); AL(v_x, Mv * W); AL(v_ln, Mv * W);
+  AL(v_qkv, Mv * 3 * W); AL(v_vt, B * heads * 64 * e->Lpad); AL(v_attn, Mv * W); AL(v_h, Mv * d.vit_mlp);
+  AL(v_out, Mv * W); AL(a_h, Mv * 2 * W); AL(a_z, Mv * H); AL(visual, Mv * H);
+  AL(slab_partial, B * 64 * 2);
+  AL(p_x, Mp * H); AL(p_ln, Mp * H); AL(p_qkv, Mp * e->qkv_cols); AL(p_attn, Mp * H); AL(p_h, Mp * I);
+  AL(d_x, B * H); AL(d_ln, B * H); AL(d_qkv, B * e->qkv_cols); AL(d_attn, B * H); AL(d_h, B * I); AL(d_last, B * H);
+  AL(logits, B * d.vocab); AL(logits_f32, B * d.vocab);
+  AL(attn_partial, B * d.n_kv_head * kMaxSplit * (32 + 16 * D));
+  e->cache_layer_stride = B * d.n_kv_head * (int64_t)e->tcap * D;
+  AL(kcache, e->cache_layer_stride * d.n_layer); AL(vtcache, e->cache_layer_stride * d.n_layer);
+  AL(state, 1); AL(params, 1); AL(seen, B * d.vocab); AL(next_ids, B); AL(out_ids, B * (int64_t)d.max_len);
+  AL(ids_tmp, B * kMaxPrompt);
+#undef AL
+  if (!ok) return false;
+  // zero the caches once: masked keys are never read as NaN (sv_attention.cu, P == 0 there)
+  cudaMemset(e->kcache, 0, (size_t)e->cache_layer_stride * d.n_layer * sizeof(bf16));
+  cudaMemset(e->vtcache, 0, (size_t)e->cache_layer_stride * d.n_layer * sizeof(bf16));
+  cudaMemset(e->state, 0, sizeof(GenState));
+  return cudaMallocHost(reinterpret_cast<void**>(&e->host_flag), 64) == cudaSuccess;
+}
+
+int do_linear(sv_engine* e, int impl, const bf16* x, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int M,
+              int N, int K, int act, cudaStream_t st) {
+  if (impl == SV_LINEAR_AUTO) impl = (M > 32 && tc05_supported(M, N, K)) ? SV_LINEAR_TCGEN05 : SV_LINEAR_ROWGROUP;
+  if (impl == SV_LINEAR_TCGEN05) {
+    if (!tc05_supported(M, N, K)) return fail(e, SV_ERR_INVALID, "tcgen05 linear needs N%%8==0, K%%64==0 (M=%d N=%d K=%d)", M, N, K);
+    cudaError_t r = launch_linear_tc05(x, w, bias, res, y, M, N, K, act, st);
+    if (r != cudaSuccess) return fail(e, SV_ERR_CUDA, "tcgen05 linear launch failed: %s", cudaGetErrorString(r));
+    return SV_OK;
+  }
+  if (K % 32 != 0) return fail(e, SV_ERR_INVALID, "rowgroup linear needs K%%32==0 (K=%d)", K);
+  launch_linear_rowgroup(x, w, bias, res, y, M, N, K, act, st);
+  return SV_OK;
+}
+#define LIN(...)                                   \
+  do {                                             \
+    int _r = do_linear(e, e->linear_impl, __VA_ARGS__); \
+    if (_r != SV_OK) return _r;                    \
+  } while (0)
+
+// ---- stage: ViT + adapter -------------------------------------------------------------------
+int run_encode(sv_engine* e, const bf16* pixels, int B, cudaStream_t st) {
+  const sv_model_desc& d = e->d;
+  const int W = d.vit_width, Q = e->Q, NP = e->NP, M = B * Q, H = d.hidden;
+  launch_im2col(pixels, e->v_patches, B, d.image_size, d.patch_size, e->Kp, st);
+  LIN(e->v_patches, e->conv_w, nullptr, nullptr, e->v_pe, B * NP, W, e->Kp, SV_ACT_NONE, st);     // conv1 (no bias)
+  launch_vit_assemble(e->v_pe, e->cls, e->pos, e->v_ln, B, NP, W, st);                             // cat + pos
+  launch_layernorm(e->v_ln, e->lnpre_w, e->lnpre_b, e->v_x, M, W, 1e-5f, W, st);                   // ln_pre
+  for (int i = 0; i < d.vit_layers; ++i) {
+    const VitLayer& L = e->vit[i];
+    launch_layernorm(e->v_x, L.ln1_w, L.ln1_b, e->v_ln, M, W, 1e-5f, W, st);
+    LIN(e->v_ln, L.qkv_w, L.qkv_b, nullptr, e->v_qkv, M, 3 * W, W, SV_ACT_NONE, st);
+    launch_vit_transpose_v(e->v_qkv, e->v_vt, B, Q, d.vit_heads, e->Lpad, st);
+    launch_attention_vit(e->v_qkv, e->v_vt, e->v_attn, B, Q, d.vit_heads, e->Lpad, st);
+    LIN(e->v_attn, L.out_w, L.out_b, e->v_x, e->v_x, M, W, W, SV_ACT_NONE, st);                    // x += attn
+    launch_layernorm(e->v_x, L.ln2_w, L.ln2_b, e->v_ln, M, W, 1e-5f, W, st);
+    LIN(e->v_ln, L.fc_w, L.fc_b, nullptr, e->v_h, M, d.vit_mlp, W, SV_ACT_QUICKGELU, st);
+    LIN(e->v_h, L.proj_w, L.proj_b, e->v_x, e->v_x, M, W, d.vit_mlp, SV_ACT_NONE, st);             // x += mlp
+  }
+  launch_layernorm(e->v_x, e->lnv_w, e->lnv_b, e->v_out, M, W, 1e-5f, W, st);                      // ln_vision
+  LIN(e->v_out, e->afc_w, e->afc_b, nullptr, e->a_h, M, 2 * W, W, SV_ACT_SILU, st);
+  LIN(e->a_h, e->aproj_w, e->aproj_b, nullptr, e->a_z, M, H, 2 * W, SV_ACT_NONE, st);
+  if (d.adapter_norm == 0)
+    launch_slab_layernorm(e->a_z, e->anorm_w, e->anorm_b, e->visual, e->slab_partial, B, (int64_t)Q * H, 1e-5f, st);
+  else
+    launch_batchnorm_tokens(e->a_z, e->anorm_w, e->anorm_b, e->anorm_rm, e->anorm_rv, e->visual, B, Q, H, 1e-5f, st);
+  return SV_OK;
+}
+
+// ---- stage: decoder prefill -----------------------------------------------------------------
+// `prefix` is [B, q, H] embeddings (the resident visual prefix, or caller-provided inputs_embeds);
+// `prompt_ids` [B, P] are embedded through wte and appended (P may be 0).
+int run_prefill(sv_engine* e, const bf16* prefix, int q, const int32_t* prompt_ids, int B, int P, cudaStream_t st) {
+  const sv_model_desc& d = e->d;
+  const int H = d.hidden, T0 = q + P, M = B * T0, D = d.head_dim;
+  launch_embed_prefix(prefix, prompt_ids, e->wte, e->wpe, e->p_x, B, q, P, H, d.vocab, st);
+  for (int i = 0; i < d.n_layer; ++i) {
+    const DecLayer& L = e->dec[i];
+    bf16* kc = e->kcache + e->cache_layer_stride * i;
+    bf16* vc = e->vtcache + e->cache_layer_stride * i;
+    launch_layernorm(e->p_x, L.ln1_w, L.ln1_b, e->p_ln, M, H, d.ln_eps, H, st);
+    LIN(e->p_ln, L.attn_w, L.attn_b, nullptr, e->p_qkv, M, e->qkv_cols, H, SV_ACT_NONE, st);
+    launch_kv_scatter(e->p_qkv, kc, vc, B, T0, d.n_head * D, d.n_kv_head, D, e->tcap, 0, st);
+    launch_attention_heads(e->p_qkv, e->qkv_cols, kc, vc, e->p_attn, B, T0, d.n_head, d.n_kv_head, D, e->tcap, st);
+    LIN(e->p_attn, L.proj_w, L.proj_b, e->p_x, e->p_x, M, H, H, SV_ACT_NONE, st);
+    launch_layernorm(e->p_x, L.ln2_w, L.ln2_b, e->p_ln, M, H, d.ln_eps, H, st);
+    LIN(e->p_ln, L.fc_w, L.fc_b, nullptr, e->p_h, M, d.n_inner, H, SV_ACT_GELU_TANH, st);
+    LIN(e->p_h, L.fc2_w, L.fc2_b, e->p_x, e->p_x, M, H, d.n_inner, SV_ACT_NONE, st);
+  }
+  // last-position logits only (HF computes all T0 positions; only [:, -1] is consumed)
+  launch_gather_rows(e->p_x, e->d_last, B, T0, T0 - 1, H, st);
+  launch_layernorm(e->d_last, e->lnf_w, e->lnf_b, e->d_ln, B, H, d.ln_eps, H, st);
+  launch_linear_rowgroup(e->d_ln, e->lm_head, nullptr, nullptr, e->logits, B, d.vocab, H, SV_ACT_NONE, st);
+  return SV_OK;
+}
+
+// ---- one decode step: token ids (device) at position state->cur_len -> logits ----------------
+int run_decode_layers(sv_engine* e, const int32_t* ids, int B, int nsplit, cudaStream_t st) {
+  const sv_model_desc& d = e->d;
+  const int H = d.hidden, D = d.head_dim;
+  launch_embed_tokens(ids, e->wte, e->wpe, e->state, e->d_x, B, H, d.vocab, d.n_positions, st);
+  for (int i = 0; i < d.n_layer; ++i) {
+    const DecLayer& L = e->dec[i];
+    bf16* kc = e->kcache + e->cache_layer_stride * i;
+    bf16* vc = e->vtcache + e->cache_layer_stride * i;
+    launch_layernorm(e->d_x, L.ln1_w, L.ln1_b, e->d_ln, B, H, d.ln_eps, H, st);
+    launch_linear_rowgroup(e->d_ln, L.attn_w, L.attn_b, nullptr, e->d_qkv, B, e->qkv_cols, H, SV_ACT_NONE, st);
+    launch_kv_append(e->d_qkv, kc, vc, e->state, B, d.n_head * D, d.n_kv_head, D, e->tcap, st);
+    launch_attention_decode(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->attn_partial, e->state, B, d.n_head,
+                            d.n_kv_head, D, e->tcap, nsplit, st);
+    launch_linear_rowgroup(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, B, H, H, SV_ACT_NONE, st);
+    launch_layernorm(e->d_x, L.ln2_w, L.ln2_b, e->d_ln, B, H, d.ln_eps, H, st);
+    launch_linear_rowgroup(e->d_ln, L.fc_w, L.fc_b, nullptr, e->d_h, B, d.n_inner, H, SV_ACT_GELU_TANH, st);
+    launch_linear_rowgroup(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, B, H, d.n_inner, SV_ACT_NONE, st);
+  }
+  launch_layernorm(e->d_x, e->lnf_w, e->lnf_b, e->d_ln, B, H, d.ln_eps, H, st);
+  launch_linear_rowgroup(e->d_ln, e->lm_head, nullptr, nullptr, e->logits, B, d.vocab, H, SV_ACT_NONE, st);
+  return SV_OK;
+}
+
+int nsplit_for(const sv_engine* e, int total_len) {
+  int blocks = (total_len + 31) / 32;
+  return std::max(1, std::min(kMaxSplit, blocks));
+}
+
+void launch_select(sv_engine* e, int B, int do_sample, cudaStream_t st) {
+  if (do_sample)
+    launch_select_sample(e->logits, e->d.vocab, B, e->state, e->params, e->seen, e->next_ids, e->out_ids,
+                         e->logits_f32, st);
+  else
+    launch_select_greedy(e->logits, e->d.vocab, B, e->state, e->params, e->seen, e->next_ids, e->out_ids, st);
+}
+
+int check_ready(sv_engine* e) {
+  for (auto& kv : e->w)
+    if (!kv.second.loaded && !kv.second.optional) return fail(e, SV_ERR_STATE, "weight not loaded: %s", kv.first.c_str());
+  return SV_OK;
+}
+
+}  // namespace
+
+static int finish_prefill_impl(sv_engine* e, int batch, int prefix_len, float* last_logits, cudaStream_t st) {
+  e->prefix_len = prefix_len;
+  e->host_cur_len = e->prefix_len;
+  GenState hs;
+  memset(&hs, 0, sizeof(hs));
+  hs.cur_len = e->prefix_len;
+  for (int b = 0; b < batch; ++b) hs.unfinished[b] = 1;
+  SV_CK(e, cudaMemcpyAsync(e->state, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));   // pageable: staged synchronously
+  if (last_logits) launch_logits_to_float(e->logits, last_logits, (int64_t)batch * e->d.vocab, st);
+  SV_CK(e, cudaGetLastError());
+  e->prefilled = true;
+  return SV_OK;
+}
+
+static int finish_prefill(sv_engine* e, int batch, int prefix_len, float* last_logits, cudaStream_t st) {
+  LaunchScope scope(e);
+  return finish_prefill_impl(e, batch, prefix_len, last_logits, st);
+}
+
+// =============================================================================================
+extern "C" {
+
+int sv_abi_version(void) { return SV_ABI_VERSION; }
+
+const char* sv_last_error(const sv_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
+  if (!desc || !out) return fail(nullptr, SV_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const sv_model_desc& d = *desc;
+  if (d.variant != 0)
+    return fail(nullptr, SV_ERR_UNSUPPORTED, "variant %d (SigLIP + StarCoder2, StarVector-8B) is not built in this round", d.variant);
+  if (d.vit_width != d.vit_heads * 64) return fail(nullptr, SV_ERR_INVALID, "ViT head dim must be 64");
+  if (d.head_dim != 128 || d.hidden != d.n_head * d.head_dim) return fail(nullptr, SV_ERR_INVALID, "decoder head dim must be 128 and hidden == n_head*128");
+  if (d.n_kv_head < 1 || d.n_head % d.n_kv_head || d.n_head / d.n_kv_head > 16) return fail(nullptr, SV_ERR_INVALID, "need 1 <= n_head/n_kv_head <= 16");
+  if (d.image_size % d.patch_size) return fail(nullptr, SV_ERR_INVALID, "image_size %% patch_size != 0");
+  if (d.vit_width % 64 || d.vit_mlp % 64 || d.hidden % 64 || d.n_inner % 64) return fail(nullptr, SV_ERR_INVALID, "widths must be multiples of 64");
+  if (d.max_batch < 1 || d.max_batch > 8) return fail(nullptr, SV_ERR_INVALID, "max_batch must be in [1,8] (decode kernels hold 8 rows per MMA)");
+  if (d.adapter_norm != 0 && d.adapter_norm != 1) return fail(nullptr, SV_ERR_INVALID, "adapter_norm must be 0 or 1");
+  if (d.vocab < 8 || d.vocab > (1 << 20)) return fail(nullptr, SV_ERR_INVALID, "vocab out of range");
+
+  int ndev = 0;
+  cudaError_t r = cudaGetDeviceCount(&ndev);
+  if (r != cudaSuccess || ndev <= device)
+    return fail(nullptr, SV_ERR_CUDA, "no CUDA device %d (%s): this engine has no CPU fallback", device,
+                r == cudaSuccess ? "device count too small" : cudaGetErrorString(r));
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, SV_ERR_CUDA, "device %d is sm_%d%d; kernels are built for sm_100a (B200) only", device, prop.major, prop.minor);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+  sv_engine* e = new sv_engine();
+  e->d = d;
+  e->device = device;
+  const int g = d.image_size / d.patch_size;
+  e->NP = g * g;
+  e->Q = e->NP + 1;
+  e->Kp = (3 * d.patch_size * d.patch_size + 63) / 64 * 64;
+  e->Lpad = (e->Q + 31) / 32 * 32;
+  e->qkv_cols = d.hidden + 2 * d.n_kv_head * d.head_dim;
+  int max_len = std::min(d.max_len, d.n_positions);
+  if (max_len < e->Q + 2) { delete e; return fail(nullptr, SV_ERR_INVALID, "max_len %d smaller than the visual prefix", d.max_len); }
+  e->d.max_len = max_len;
+  e->tcap = (max_len + 1 + 31) / 32 * 32;
+  const char* impl = getenv("SV_LINEAR_IMPL");
+  if (impl && !strcmp(impl, "rowgroup")) e->linear_impl = SV_LINEAR_ROWGROUP;
+  if (impl && !strcmp(impl, "tcgen05")) e->linear_impl = SV_LINEAR_TCGEN05;
+  if (!build_weights(e) || !build_buffers(e)) {
+    std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    sv_engine_destroy(e);
+    return fail(nullptr, SV_ERR_CUDA, "%s", msg.c_str());
+  }
+  if (cudaStreamCreateWithFlags(&e->gen_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&e->ev_t0) != cudaSuccess || cudaEventCreate(&e->ev_t1) != cudaSuccess) {
+    sv_engine_destroy(e);
+    return fail(nullptr, SV_ERR_CUDA, "stream/event creation failed");
+  }
+  *out = e;
+  return SV_OK;
+}
+
+void sv_engine_destroy(sv_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& g : e->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->host_flag) cudaFreeHost(e->host_flag);
+  if (e->gen_stream) cudaStreamDestroy(e->gen_stream);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+  if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+  delete e;
+}
+
+int sv_engine_load_weight(sv_engine* e, const char* hf_name, const void* data, const int64_t* shape, int32_t ndim,
+                          int32_t dtype) {
+  if (!e || !hf_name || !data || !shape) return fail(e, SV_ERR_INVALID, "null argument");
+  SV_CK(e, cudaSetDevice(e->device));
+  LaunchScope scope(e);
+  std::string name = hf_name;
+  auto ends_with = [&](const char* s) { size_t n = strlen(s); return name.size() >= n && !name.compare(name.size() - n, n, s); };
+  if (ends_with("num_batches_tracked") || ends_with(".attn.bias") || ends_with("transformer.bias") ||
+      ends_with(".attn.masked_bias"))
+    return SV_OK;   // buffers that carry no parameters
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  if (name == LMH && e->w.find(name) == e->w.end()) {   // explicit (un-tied) lm_head
+    const sv_model_desc& d = e->d;
+    bf16* p = add_weight(e, name, {(int64_t)d.vocab, (int64_t)d.hidden}, -1, true);
+    if (!p) return fail(e, SV_ERR_CUDA, "allocation failed for lm_head");
+    e->lm_head = p;
+  }
+  auto it = e->w.find(name);
+  if (it == e->w.end()) return fail(e, SV_ERR_INVALID, "unknown weight name: %s", hf_name);
+  Weight& wt = it->second;
+  if (numel != wt.numel || ndim != (int)wt.shape.size())
+    return fail(e, SV_ERR_INVALID, "shape mismatch for %s: got %lld elements / %d dims, expected %lld / %zu", hf_name,
+                (long long)numel, ndim, (long long)wt.numel, wt.shape.size());
+  for (int i = 0; i < ndim; ++i)
+    if (shape[i] != wt.shape[i]) return fail(e, SV_ERR_INVALID, "shape mismatch for %s at dim %d", hf_name, i);
+  if (dtype == SV_DTYPE_BF16) {
+    SV_CK(e, cudaMemcpy(wt.p, data, (size_t)numel * 2, cudaMemcpyDefault));
+  } else if (dtype == SV_DTYPE_F32 || dtype == SV_DTYPE_F16) {
+    const size_t es = dtype == SV_DTYPE_F32 ? 4 : 2;
+    void* tmp = nullptr;
+    SV_CK(e, cudaMalloc(&tmp, (size_t)numel * es));
+    cudaError_t r = cudaMemcpy(tmp, data, (size_t)numel * es, cudaMemcpyDefault);
+    if (r == cudaSuccess) {
+      launch_convert_to_bf16(tmp, dtype, wt.p, numel, nullptr);
+      r = cudaDeviceSynchronize();
+    }
+    cudaFree(tmp);
+    SV_CK(e, r);
+  } else {
+    return fail(e, SV_ERR_INVALID, "unsupported dtype %d", dtype);
+  }
+  if (wt.p == e->conv_raw) {   // [W,3,p,p] -> [W, Kp] zero padded GEMM operand
+    launch_pad_rows(e->conv_raw, e->conv_w, e->d.vit_width, 3 * e->d.patch_size * e->d.patch_size, e->Kp, nullptr);
+    SV_CK(e, cudaDeviceSynchronize());
+  }
+  wt.loaded = true;
+  return SV_OK;
+}
+
+int sv_engine_missing_weights(sv_engine* e) {
+  if (!e) return SV_ERR_INVALID;
+  int n = 0;
+  std::string names;
+  for (auto& kv : e->w)
+    if (!kv.second.loaded && !kv.second.optional) { ++n; names += kv.first + "\n"; }
+  e->err = names;
+  return n;
+}
+
+int sv_encode_images(sv_engine* e, const void* pixels, int32_t batch, void* out_embeds, void* vit_out, void* stream) {
+  if (!e || !pixels) return fail(e, SV_ERR_INVALID, "null argument");
+  if (batch < 1 || batch > e->d.max_batch) return fail(e, SV_ERR_INVALID, "batch %d outside [1,%d]", batch, e->d.max_batch);
+  int r = check_ready(e);
+  if (r != SV_OK) return r;
+  SV_CK(e, cudaSetDevice(e->device));
+  LaunchScope scope(e);
+  cudaStream_t st = (cudaStream_t)stream;
+  r = run_encode(e, (const bf16*)pixels, batch, st);
+  if (r != SV_OK) return r;
+  const size_t M = (size_t)batch * e->Q;
+  if (out_embeds) SV_CK(e, cudaMemcpyAsync(out_embeds, e->visual, M * e->d.hidden * 2, cudaMemcpyDeviceToDevice, st));
+  if (vit_out) SV_CK(e, cudaMemcpyAsync(vit_out, e->v_out, M * e->d.vit_width * 2, cudaMemcpyDeviceToDevice, st));
+  SV_CK(e, cudaGetLastError());
+  e->cur_batch = batch;
+  e->encoded = true;
+  e->prefilled = false;
+  return SV_OK;
+}
+
+int sv_prefill(sv_engine* e, const int32_t* prompt_ids, int32_t batch, int32_t prompt_len, float* last_logits,
+               void* stream) {
+  if (!e || !prompt_ids) return fail(e, SV_ERR_INVALID, "null argument");
+  if (!e->encoded || batch != e->cur_batch) return fail(e, SV_ERR_STATE, "sv_prefill needs sv_encode_images with the same batch first");
+  if (prompt_len < 1 || prompt_len > kMaxPrompt) return fail(e, SV_ERR_INVALID, "prompt_len %d outside [1,%d]", prompt_len, kMaxPrompt);
+  if (e->Q + prompt_len + 1 > e->d.max_len) return fail(e, SV_ERR_INVALID, "prefix longer than max_len");
+  SV_CK(e, cudaSetDevice(e->device));
+  LaunchScope scope(e);
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = run_prefill(e, e->visual, e->Q, prompt_ids, batch, prompt_len, st);
+  if (r != SV_OK) return r;
+  return finish_prefill(e, batch, e->Q + prompt_len, last_logits, st);
+}
+
+int sv_prefill_embeds(sv_engine* e, const void* inputs_embeds, int32_t batch, int32_t seq_len, float* last_logits,
+                      void* stream) {
+  if (!e || !inputs_embeds) return fail(e, SV_ERR_INVALID, "null argument");
+  if (batch < 1 || batch > e->d.max_batch) return fail(e, SV_ERR_INVALID, "batch %d outside [1,%d]", batch, e->d.max_batch);
+  if (seq_len < 1 || seq_len > e->Q + kMaxPrompt) return fail(e, SV_ERR_INVALID, "seq_len %d outside [1,%d]", seq_len, e->Q + kMaxPrompt);
+  if (seq_len + 1 > e->d.max_len) return fail(e, SV_ERR_INVALID, "prefix longer than max_len");
+  int r = check_ready(e);
+  if (r != SV_OK) return r;
+  SV_CK(e, cudaSetDevice(e->device));
+  LaunchScope scope(e);
+  cudaStream_t st = (cudaStream_t)stream;
+  r = run_prefill(e, (const bf16*)inputs_embeds, seq_len, nullptr, batch, 0, st);
+  if (r != SV_OK) return r;
+  e->cur_batch = batch;
+  return finish_prefill(e, batch, seq_len, last_logits, st);
+}
+
+int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream) {
+  if (!e || !ids) return fail(e, SV_ERR_INVALID, "null argument");
+  if (!e->prefilled) return fail(e, SV_ERR_STATE, "sv_decode_step needs sv_prefill first");
+  if (e->host_cur_len + 1 > e->d.max_len) return fail(e, SV_ERR_INVALID, "KV cache full (max_len %d)", e->d.max_len);
+  SV_CK(e, cudaSetDevice(e->device));
+  LaunchScope scope(e);
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = run_decode_layers(e, ids, e->cur_batch, nsplit_for(e, e->host_cur_len + 1), st);
+  if (r != SV_OK) return r;
+  launch_advance_len(e->state, st);
+  if (logits) launch_logits_to_float(e->logits, logits, (int64_t)e->cur_batch * e->d.vocab, st);
+  SV_CK(e, cudaGetLastError());
+  e->host_cur_len += 1;
+  return SV_OK;
+}
+
+int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t* out_len, void* stream) {
+  if (!e || !p || !out_ids) return fail(e, SV_ERR_INVALID, "null argument");
+  if (!e->prefilled) return fail(e, SV_ERR_STATE, "sv_generate needs sv_prefill first");
+  if (e->host_cur_len != e->prefix_len) return fail(e, SV_ERR_STATE, "sv_generate must directly follow sv_prefill");
+  const int B = e->cur_batch, max_new = p->max_new_tokens;
+  if (max_new < 1) return fail(e, SV_ERR_INVALID, "max_new_tokens must be >= 1");
+  if (e->prefix_len + max_new > e->d.max_len)
+    return fail(e, SV_ERR_INVALID, "prefix %d + max_new_tokens %d exceeds max_len %d", e->prefix_len, max_new, e->d.max_len);
+  if (p->n_stop_ids < 0 || p->n_stop_ids > 8) return fail(e, SV_ERR_INVALID, "n_stop_ids outside [0,8]");
+  if (p->do_sample && !(p->temperature > 0.f)) return fail(e, SV_ERR_INVALID, "temperature must be > 0");
+  if (!(p->repetition_penalty > 0.f)) return fail(e, SV_ERR_INVALID, "repetition_penalty must be > 0");
+  SV_CK(e, cudaSetDevice(e->device));
+  LaunchScope scope(e);
+  cudaStream_t caller = (cudaStream_t)stream, st = e->gen_stream;
+  SV_CK(e, cudaEventRecord(e->ev_in, caller));
+  SV_CK(e, cudaStreamWaitEvent(st, e->ev_in, 0));
+
+  GenParamsDev hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.max_new = max_new; hp.do_sample = p->do_sample; hp.eos_id = p->eos_token_id; hp.pad_id = p->pad_token_id;
+  hp.n_stop = p->n_stop_ids;
+  for (int i = 0; i < p->n_stop_ids; ++i) hp.stop_ids[i] = p->stop_ids[i];
+  hp.stop_row0_only = p->stop_row0_only; hp.out_stride = e->d.max_len;
+  hp.temperature = p->temperature; hp.top_p = p->top_p; hp.rep_penalty = p->repetition_penalty; hp.seed = p->seed;
+  SV_CK(e, cudaMemcpyAsync(e->params, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
+  SV_CK(e, cudaMemsetAsync(e->seen, 0, (size_t)B * e->d.vocab, st));
+  launch_fill_i32(e->out_ids, p->pad_token_id, B * e->d.max_len, st);
+
+  // token 0 comes from the prefill logits
+  launch_select(e, B, p->do_sample, st);
+  launch_gen_finalize(e->state, e->params, B, /*advance_len=*/0, st);
+
+  const int nsplit = nsplit_for(e, e->prefix_len + max_new);
+  const long long key = (long long)B * 1000 + nsplit * 2 + (p->do_sample ? 1 : 0);
+  GraphEntry& ge = e->graphs[key];
+  if (!ge.exec && max_new > 1) {
+    int64_t counted = 0;
+    g_launch_counter = &counted;
+    cudaGraph_t graph = nullptr;
+    SV_CK(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int r = run_decode_layers(e, e->next_ids, B, nsplit, st);
+    launch_select(e, B, p->do_sample, st);
+    launch_gen_finalize(e->state, e->params, B, /*advance_len=*/1, st);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    g_launch_counter = &e->launches;
+    if (r != SV_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    SV_CK(e, ce);
+    ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    SV_CK(e, ce);
+    ge.kernels = (int)counted;
+  }
+
+  const int poll = p->poll_interval > 0 ? p->poll_interval : 16;
+  SV_CK(e, cudaEventRecord(e->ev_t0, st));
+  int steps = 0;
+  bool done = false;
+  for (int s = 1; s < max_new && !done; ++s) {
+    SV_CK(e, cudaGraphLaunch(ge.exec, st));
+    e->launches += ge.kernels;
+    ++steps;
+    if ((p->eos_token_id >= 0 || p->n_stop_ids > 0) && (s % poll == 0)) {
+      SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->done, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      SV_CK(e, cudaStreamSynchronize(st));
+      done = e->host_flag[0] != 0;
+    }
+  }
+  SV_CK(e, cudaEventRecord(e->ev_t1, st));
+  // rectangular result: [B, n_generated] new tokens, padded (HF returns the same rectangle)
+  SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->step, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  SV_CK(e, cudaStreamSynchronize(st));
+  const int n_gen = std::min(e->host_flag[0], max_new);
+  SV_CK(e, cudaMemcpy2DAsync(out_ids, (size_t)max_new * 4, e->out_ids, (size_t)e->d.max_len * 4, (size_t)max_new * 4, B,
+                             cudaMemcpyDeviceToDevice, st));
+  if (out_len) launch_fill_i32(out_len, n_gen, B, st);
+  SV_CK(e, cudaStreamSynchronize(st));
+  SV_CK(e, cudaGetLastError());
+  SV_CK(e, cudaEventElapsedTime(&e->last_decode_ms, e->ev_t0, e->ev_t1));
+  e->last_decode_steps = steps;
+  e->host_cur_len = e->prefix_len + std::max(0, n_gen - 1);
+  e->prefilled = false;   // the cache now holds a finished generation; a new prefill is required
+  return SV_OK;
+}
+
+int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_t batch, const int32_t* prompt_ids_host,
+                            int32_t prompt_len, const sv_gen_params* p, int32_t* out_ids_host, int32_t* out_len_host,
+                            void* stream) {
+  if (!e || !pixels_host || !prompt_ids_host || !p || !out_ids_host) return fail(e, SV_ERR_INVALID, "null argument");
+  if (batch < 1 || batch > e->d.max_batch) return fail(e, SV_ERR_INVALID, "batch %d outside [1,%d]", batch, e->d.max_batch);
+  if (prompt_len < 1 || prompt_len > kMaxPrompt) return fail(e, SV_ERR_INVALID, "prompt_len outside [1,%d]", kMaxPrompt);
+  SV_CK(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t px_bytes = (size_t)batch * 3 * e->d.image_size * e->d.image_size * 2;
+  bf16* px = nullptr;
+  int32_t *dout = nullptr, *dlen = nullptr;
+  SV_CK(e, cudaMalloc(reinterpret_cast<void**>(&px), px_bytes));
+  cudaError_t ce = cudaMalloc(reinterpret_cast<void**>(&dout), ((size_t)batch * p->max_new_tokens + batch) * 4);
+  if (ce != cudaSuccess) { cudaFree(px); SV_CK(e, ce); }
+  dlen = dout + (size_t)batch * p->max_new_tokens;
+  int r = SV_OK;
+  ce = cudaMemcpyAsync(px, pixels_host, px_bytes, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->ids_tmp, prompt_ids_host, (size_t)batch * prompt_len * 4, cudaMemcpyHostToDevice, st);
+  if (ce != cudaSuccess) r = fail(e, SV_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(ce));
+  if (r == SV_OK) r = sv_encode_images(e, px, batch, nullptr, nullptr, stream);
+  if (r == SV_OK) r = sv_prefill(e, e->ids_tmp, batch, prompt_len, nullptr, stream);
+  if (r == SV_OK) r = sv_generate(e, p, dout, dlen, stream);
+  if (r == SV_OK) {
+    ce = cudaMemcpyAsync(out_ids_host, dout, (size_t)batch * p->max_new_tokens * 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess && out_len_host) ce = cudaMemcpyAsync(out_len_host, dlen, (size_t)batch * 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) r = fail(e, SV_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(ce));
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(px);
+  cudaFree(dout);
+  return r;
+}
+
+int64_t sv_launch_count(const sv_engine* e) { return e ? e->launches : 0; }
+
+int sv_last_decode_timing(const sv_engine* e, float* ms, int32_t* steps) {
+  if (!e) return SV_ERR_INVALID;
+  if (ms) *ms = e->last_decode_ms;
+  if (steps) *steps = e->last_decode_steps;
+  return SV_OK;
+}
+
+// ---- single-kernel entry points ---------------------------------------------------------------
+static std::string g_op_error;
+static int op_fail(const char* what, cudaError_t r) {
+  g_create_error = std::string(what) + ": " + cudaGetErrorString(r);
+  return SV_ERR_CUDA;
+}
+
+int sv_op_layernorm(const void* x, const void* w, const void* b, void* y, int32_t rows, int32_t cols, float eps,
+                    void* stream) {
+  if (!x || !w || !b || !y || cols % 8) return fail(nullptr, SV_ERR_INVALID, "bad layernorm arguments");
+  launch_layernorm((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, cols, eps, cols, (cudaStream_t)stream);
+  cudaError_t r = cudaGetLastError();
+  return r == cudaSuccess ? SV_OK : op_fail("layernorm", r);
+}
+
+int sv_op_linear(int32_t impl, const void* x, const void* w, const void* bias, const void* residual, void* y, int32_t M,
+                 int32_t N, int32_t K, int32_t act, void* stream) {
+  if (!x || !w || !y || M < 1 || N < 1 || K < 32) return fail(nullptr, SV_ERR_INVALID, "bad linear arguments");
+  int r = do_linear(nullptr, impl, (const bf16*)x, (const bf16*)w, (const bf16*)bias, (const bf16*)residual, (bf16*)y, M,
+                    N, K, act, (cudaStream_t)stream);
+  if (r != SV_OK) return r;
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? SV_OK : op_fail("linear", ce);
+}
+
+int sv_op_attention_vit(const void* qkv, void* out, int32_t batch, int32_t seq, int32_t heads, void* stream) {
+  if (!qkv || !out || batch < 1 || seq < 1 || heads < 1) return fail(nullptr, SV_ERR_INVALID, "bad attention arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int seq_pad = (seq + 31) / 32 * 32;
+  bf16* vt = nullptr;
+  cudaError_t r = cudaMalloc(reinterpret_cast<void**>(&vt), (size_t)batch * heads * 64 * seq_pad * 2);
+  if (r != cudaSuccess) return op_fail("attention_vit alloc", r);
+  launch_vit_transpose_v((const bf16*)qkv, vt, batch, seq, heads, seq_pad, st);
+  launch_attention_vit((const bf16*)qkv, vt, (bf16*)out, batch, seq, heads, seq_pad, st);
+  r = cudaStreamSynchronize(st);
+  cudaFree(vt);
+  return r == cudaSuccess ? SV_OK : op_fail("attention_vit", r);
+}
+
+int sv_op_attention_mqa(const void* qkv, void* out, int32_t batch, int32_t seq, int32_t heads, void* stream) {
+  if (!qkv || !out || batch < 1 || seq < 1 || heads < 1 || heads > 16) return fail(nullptr, SV_ERR_INVALID, "bad attention arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = 128, tcap = (seq + 31) / 32 * 32;
+  const size_t n = (size_t)batch * tcap * D;
+  bf16* kc = nullptr;
+  cudaError_t r = cudaMalloc(reinterpret_cast<void**>(&kc), 2 * n * 2);
+  if (r != cudaSuccess) return op_fail("attention_mqa alloc", r);
+  bf16* vc = kc + n;
+  cudaMemsetAsync(kc, 0, 2 * n * 2, st);
+  launch_kv_scatter((const bf16*)qkv, kc, vc, batch, seq, heads * D, 1, D, tcap, 0, st);
+  launch_attention_heads((const bf16*)qkv, heads * D + 2 * D, kc, vc, (bf16*)out, batch, seq, heads, 1, D, tcap, st);
+  r = cudaStreamSynchronize(st);
+  cudaFree(kc);
+  return r == cudaSuccess ? SV_OK : op_fail("attention_mqa", r);
+}
+
+}  // extern "C"

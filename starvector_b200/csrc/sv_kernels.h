@@ -1,0 +1,81 @@
+// Launcher declarations shared by the kernel translation units and sv_engine.cu.
+// All tensors are bf16 unless noted; `st` is the stream every launch goes to.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sv_common.cuh"
+
+namespace sv {
+
+// Counts kernel launches issued through the launchers (sv_launch_count()).
+extern thread_local int64_t* g_launch_counter;
+inline void count_launch(int n = 1) { if (g_launch_counter) *g_launch_counter += n; }
+
+// Device-resident generation state, read/written by kernels so a captured graph can be replayed.
+struct GenState {
+  int32_t cur_len;      // tokens in the KV cache == position of the token fed next
+  int32_t step;         // generated tokens so far == next free column of out_ids
+  int32_t done;         // all rows finished (or row-0 stop fired)
+  int32_t row0_stop;    // scratch: row 0 matched the stop sequence this step
+  int32_t unfinished[64];
+};
+
+struct GenParamsDev {
+  int32_t max_new, do_sample, eos_id, pad_id, n_stop, stop_ids[8], stop_row0_only, out_stride;
+  float temperature, top_p, rep_penalty;
+  unsigned long long seed;
+};
+
+// ---- sv_kernels_basic.cu
+void launch_layernorm(const bf16* x, const bf16* w, const bf16* b, bf16* y, int rows, int cols, float eps,
+                      int64_t x_row_stride, cudaStream_t st);
+void launch_convert_to_bf16(const void* src, int dtype, bf16* dst, int64_t n, cudaStream_t st);
+void launch_pad_rows(const bf16* src, bf16* dst, int rows, int src_cols, int dst_cols, cudaStream_t st);
+void launch_im2col(const bf16* pixels, bf16* patches, int batch, int image, int patch, int kpad, cudaStream_t st);
+void launch_vit_assemble(const bf16* pe, const bf16* cls, const bf16* pos, bf16* x, int batch, int np, int width,
+                         cudaStream_t st);
+void launch_vit_transpose_v(const bf16* qkv, bf16* vt, int batch, int seq, int heads, int seq_pad, cudaStream_t st);
+void launch_slab_layernorm(const bf16* z, const bf16* w, const bf16* b, bf16* y, float* partial, int batch,
+                           int64_t slab, float eps, cudaStream_t st);
+void launch_batchnorm_tokens(const bf16* z, const bf16* w, const bf16* b, const bf16* rmean, const bf16* rvar, bf16* y,
+                             int batch, int q, int h, float eps, cudaStream_t st);
+void launch_embed_prefix(const bf16* visual, const int32_t* prompt_ids, const bf16* wte, const bf16* wpe, bf16* x,
+                         int batch, int q, int p, int h, int vocab, cudaStream_t st);
+void launch_embed_tokens(const int32_t* ids, const bf16* wte, const bf16* wpe, const GenState* state, bf16* x,
+                         int batch, int h, int vocab, int n_positions, cudaStream_t st);
+void launch_kv_scatter(const bf16* qkv, bf16* kcache, bf16* vtcache, int batch, int seq, int q_cols, int n_kv, int d,
+                       int tcap, int max_batch_unused, cudaStream_t st);
+void launch_kv_append(const bf16* qkv, bf16* kcache, bf16* vtcache, const GenState* state, int batch, int q_cols,
+                      int n_kv, int d, int tcap, cudaStream_t st);
+void launch_gather_rows(const bf16* x, bf16* y, int batch, int seq, int row, int h, cudaStream_t st);
+void launch_logits_to_float(const bf16* logits, float* out, int64_t n, cudaStream_t st);
+void launch_select_greedy(const bf16* logits, int vocab, int batch, GenState* state, const GenParamsDev* params,
+                          uint8_t* seen, int32_t* next_ids, int32_t* out_ids, cudaStream_t st);
+void launch_select_sample(const bf16* logits, int vocab, int batch, GenState* state, const GenParamsDev* params,
+                          uint8_t* seen, int32_t* next_ids, int32_t* out_ids, float* probs, cudaStream_t st);
+void launch_gen_finalize(GenState* state, const GenParamsDev* params, int batch, int advance_len, cudaStream_t st);
+void launch_advance_len(GenState* state, cudaStream_t st);
+void launch_fill_i32(int32_t* p, int32_t v, int n, cudaStream_t st);
+
+// ---- sv_gemm_rowgroup.cu : y[M,N] = epi(x[M,K] . w[N,K]^T) with mma.sync, weight streaming
+void launch_linear_rowgroup(const bf16* x, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int M, int N,
+                            int K, int act, cudaStream_t st);
+
+// ---- sv_gemm_tc05.cu : same contract on tcgen05 + TMA + TMEM (M >= 1, N % 8 == 0, K % 64 == 0)
+bool tc05_supported(int M, int N, int K);
+// returns cudaSuccess or the error of tensor-map creation / launch
+cudaError_t launch_linear_tc05(const bf16* x, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int M, int N,
+                               int K, int act, cudaStream_t st);
+
+// ---- sv_attention.cu
+void launch_attention_vit(const bf16* qkv, const bf16* vt, bf16* out, int batch, int seq, int heads, int seq_pad,
+                          cudaStream_t st);
+// causal attention of `seq` new tokens per row against the cache (prefill: cache already holds them)
+void launch_attention_heads(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache, bf16* out,
+                            int batch, int seq, int n_head, int n_kv, int d, int tcap, cudaStream_t st);
+void launch_attention_decode(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache, bf16* out,
+                             float* partial, const GenState* state, int batch, int n_head, int n_kv, int d, int tcap,
+                             int nsplit, cudaStream_t st);
+
+}  // namespace sv

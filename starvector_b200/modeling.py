@@ -1,0 +1,264 @@
+"""Drop-in facade: the reference's `StarVectorForCausalLM` surface on top of the B200 engine.
+
+Kept surface (reference starvector/model/starvector_arch.py:133-193,
+starvector/model/models/starvector_base.py:203-295, starvector_v1.py):
+  StarVectorForCausalLM.from_pretrained / .from_config, .cuda()/.to()/.eval(), .process_images,
+  .generate_im2svg(batch, **kw) -> list[str], .model.generate_im2svg, .model.generate_im2svg_grpo,
+  .model.svg_transformer.tokenizer, .model.svg_transformer.transformer.generate(inputs_embeds=...),
+  .model.processor, .model.query_length, .model.max_length, .model.image_encoder, .model.image_projection.
+Errors are Python exceptions (ValueError for bad arguments, RuntimeError subclasses for CUDA
+failures), as the reference's callers expect (serve/model_worker.py:183-207).
+"""
+from __future__ import annotations
+
+import json
+import os
+import warnings
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from .config import ModelDims, StarVectorConfig
+from .engine import Engine, GenerationParams
+from .tokenizer import load_tokenizer
+from .weights import DEC, synthetic_state_dict
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+class _Transformer:
+    """Stands where `svg_transformer.transformer` (the HF causal LM) is; only `.generate` is offered."""
+
+    def __init__(self, owner: "StarVectorStarCoder"):
+        self._o = owner
+        self.config = owner.llm_config
+
+    def generate(self, inputs_embeds: torch.Tensor = None, attention_mask: torch.Tensor = None, **kw) -> torch.Tensor:
+        """`GenerationMixin.generate(inputs_embeds=...)` (starvector_base.py:255): returns NEW token ids only."""
+        if inputs_embeds is None:
+            raise ValueError("generate() on this engine takes inputs_embeds (the im2svg path); input_ids-only is not built")
+        if attention_mask is not None and not bool(torch.all(attention_mask == 1)):
+            raise NotImplementedError("padded prefixes never occur on the im2svg path and are not built")
+        o = self._o
+        params = o._gen_params(kw, prefix_len=inputs_embeds.shape[1])
+        o.engine.prefill_embeds(inputs_embeds)
+        return o.engine.generate(params).long()
+
+
+class _SvgTransformer:
+    """`StarCoderModel` stand-in (llm/starcoder.py): tokenizer + transformer + prompt."""
+
+    def __init__(self, owner: "StarVectorStarCoder", tokenizer):
+        self.tokenizer = tokenizer
+        self.transformer = _Transformer(owner)
+        self.prompt = "<svg"                                   # starcoder.py:38
+        self.svg_start_token = "<svg-start>"
+
+
+class _ImageEncoder:
+    """`ImageEncoder` stand-in: `process_images` (image_encoder.py:112-117) and a callable forward."""
+
+    def __init__(self, owner: "StarVectorStarCoder"):
+        self._o = owner
+
+    def process_images(self, images) -> List[torch.Tensor]:
+        return [self._o.processor(im).unsqueeze(0) for im in images]
+
+    def __call__(self, image: torch.Tensor) -> torch.Tensor:
+        _, vit = self._o.engine.encode_images(image, return_vit=True)
+        return vit
+
+
+class ImageTrainProcessor:
+    """RGBA->white, pad to square (white), bicubic resize, ToTensor, CLIP normalise (data/util.py:40-66)."""
+
+    def __init__(self, size: int = 224):
+        self.size = size
+
+    def __call__(self, img) -> torch.Tensor:
+        from PIL import Image
+        import numpy as np
+
+        if img.mode == "RGBA":
+            bg = Image.new("RGB", img.size, (255, 255, 255))
+            bg.paste(img, mask=img.split()[3])
+            img = bg
+        img = img.convert("RGB")
+        w, h = img.size
+        m = max(w, h)
+        if w != h:
+            sq = Image.new("RGB", (m, m), (255, 255, 255))
+            sq.paste(img, ((m - w) // 2, (m - h) // 2))
+            img = sq
+        if img.size != (self.size, self.size):
+            img = img.resize((self.size, self.size), Image.BICUBIC)
+        x = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255.0)
+        mean = torch.tensor(CLIP_MEAN).view(3, 1, 1)
+        std = torch.tensor(CLIP_STD).view(3, 1, 1)
+        return (x - mean) / std
+
+
+class StarVectorStarCoder:
+    """v1 model core (models/starvector_v1.py + starvector_base.py) bound to one Engine."""
+
+    def __init__(self, config: StarVectorConfig, engine: Engine, tokenizer, wte: torch.Tensor):
+        self.config = config
+        self.engine = engine
+        self.task = "im2svg"
+        self.query_length = engine.query_length
+        self.max_length = config.max_length_train - self.query_length - 4      # starvector_base.py:41
+        self.llm_config = {"hidden_size": engine.dims.hidden, "vocab_size": engine.dims.vocab,
+                           "n_positions": engine.dims.n_positions}
+        self.processor = ImageTrainProcessor(size=engine.dims.image_size)
+        self.svg_transformer = _SvgTransformer(self, tokenizer)
+        self.image_encoder = _ImageEncoder(self)
+        self.image_projection = self._project
+        self._wte = wte                                                        # [V,H] on device, for _get_embeddings
+        self.eos_token_id: Optional[int] = tokenizer.eos_token_id
+        self.seed = 0
+
+    # -- reference helpers ---------------------------------------------------------------
+    def _project(self, *_a, **_k):
+        raise NotImplementedError("the adapter runs fused with the image encoder: use engine.encode_images(..., return_embeds=True)")
+
+    def _get_embeddings(self, input_ids: torch.Tensor) -> torch.Tensor:       # starvector_v1.py:16-18
+        return self._wte[input_ids.to(self._wte.device)]
+
+    def _tokenize_prompt(self, prompt: Optional[str], batch: int) -> torch.Tensor:
+        if prompt is None:
+            prompt = self.svg_transformer.prompt
+        enc = self.svg_transformer.tokenizer([prompt] * batch, add_special_tokens=False, return_tensors="pt",
+                                             padding="longest", truncation=True)
+        return enc["input_ids"]
+
+    def _stop_ids(self) -> List[int]:
+        return list(self.svg_transformer.tokenizer("</svg>", add_special_tokens=False)["input_ids"])   # base:226
+
+    def _gen_params(self, kw: Dict[str, Any], prefix_len: int) -> GenerationParams:
+        """`_get_generation_kwargs` (:223-241) + `_get_im2svg_specific_kwargs` (:289-295) + HF length fix-up."""
+        do_sample = bool(kw.get("use_nucleus_sampling", kw.get("do_sample", True)))
+        num_beams = int(kw.get("num_beams", 2))
+        if num_beams != 1:
+            warnings.warn(
+                f"num_beams={num_beams}: beam search / beam-sample is not built yet (SURVEY.md §8f-1); decoding with "
+                "num_beams=1. Pass num_beams=1 to silence this.", RuntimeWarning, stacklevel=3)
+        max_length = int(kw.get("max_length", 30))
+        max_new = kw.get("max_new_tokens")
+        if max_new is None:
+            max_new = max_length - prefix_len                                  # generation/utils.py:1629-1638
+        if max_new <= 0:
+            raise ValueError(
+                f"Input length of input_ids is 0, but `max_length` is set to {max_length - prefix_len}. "
+                "Increase max_length (it counts the visual prefix and the prompt).")
+        tok = self.svg_transformer.tokenizer
+        return GenerationParams(
+            max_new_tokens=int(max_new), do_sample=do_sample,
+            temperature=float(kw.get("temperature", 1)), top_p=float(kw.get("top_p", 0.9)) if do_sample else 1.0,
+            repetition_penalty=float(kw.get("repetition_penalty", 1.0)),
+            eos_token_id=self.eos_token_id, pad_token_id=tok.pad_token_id,
+            stop_ids=kw.get("stop_ids", self._stop_ids()), stop_row0_only=True,
+            seed=int(kw.get("seed", self.seed)),
+        )
+
+    # -- the path ------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate_im2svg_ids(self, batch: Dict[str, torch.Tensor], **kwargs) -> torch.Tensor:
+        """Token ids `[B, P + n_new]` (prompt + generated) — starvector_base.py:243-256."""
+        image = batch["image"]
+        prompt_ids = self._tokenize_prompt(kwargs.get("prompt"), image.shape[0])
+        params = self._gen_params(kwargs, prefix_len=self.query_length + prompt_ids.shape[1])
+        self.engine.encode_images(image)
+        self.engine.prefill(prompt_ids)
+        out = self.engine.generate(params)
+        return torch.cat([prompt_ids.to(out.device), out.long()], dim=1)
+
+    def generate_im2svg(self, batch: Dict[str, torch.Tensor], **kwargs) -> List[str]:
+        ids = self.generate_im2svg_ids(batch, **kwargs)
+        return self.svg_transformer.tokenizer.batch_decode(ids, skip_special_tokens=True)          # :257
+
+    def generate_im2svg_grpo(self, batch, **kwargs):                                               # :261-286
+        if kwargs.get("num_return_sequences", 1) != 1:
+            raise NotImplementedError("num_return_sequences > 1 is not built (SURVEY.md §8f-4)")
+        kwargs.setdefault("num_beams", 1)
+        ids = self.generate_im2svg_ids(batch, **kwargs)
+        emb, _ = self.engine.encode_images(batch["image"], return_embeds=True)
+        return {"raw_svg": self.svg_transformer.tokenizer.batch_decode(ids, skip_special_tokens=True),
+                "outputs": ids, "inputs_embeds": emb}
+
+
+class StarVectorForCausalLM:
+    """`StarVectorForCausalLM` facade (starvector_arch.py:133-193) — not an nn.Module: weights live in the engine."""
+
+    config_class = StarVectorConfig
+
+    def __init__(self, config: StarVectorConfig, state_dict: Dict[str, torch.Tensor], device: int = 0,
+                 max_batch: int = 8, max_len: Optional[int] = None, tokenizer_path: Optional[str] = None):
+        self.config = config
+        dims = config.to_dims(max_batch=max_batch, max_len=max_len)
+        self.dims = dims
+        engine = Engine(dims, device)
+        engine.load_state_dict(state_dict)
+        wte = state_dict[DEC + "wte.weight"].to(device=engine.device, dtype=torch.bfloat16)
+        tok = load_tokenizer(tokenizer_path, dims.vocab)
+        self.model = StarVectorStarCoder(config, engine, tok, wte)
+        self.device = engine.device
+        self.dtype = torch.bfloat16
+
+    # -- construction --------------------------------------------------------------------
+    @classmethod
+    def from_config(cls, config: Optional[StarVectorConfig] = None, dims: Optional[ModelDims] = None, seed: int = 0,
+                    init: str = "hf_default", device: int = 0, max_batch: int = 8, max_len: Optional[int] = None,
+                    state_dict: Optional[Dict[str, torch.Tensor]] = None) -> "StarVectorForCausalLM":
+        """Random-init model of the configured architecture (synthetic benchmark / tests)."""
+        config = config or StarVectorConfig()
+        if dims is not None:
+            config.engine_dims = {k: v for k, v in dims.__dict__.items() if k not in ("max_batch", "max_len")}
+            max_batch, max_len = dims.max_batch, dims.max_len
+        d = config.to_dims(max_batch=max_batch, max_len=max_len)
+        sd = state_dict if state_dict is not None else synthetic_state_dict(d, seed=seed, init=init)
+        return cls(config, sd, device=device, max_batch=max_batch, max_len=max_len)
+
+    @classmethod
+    def from_pretrained(cls, path: str, torch_dtype: Any = None, device: int = 0, max_batch: int = 8,
+                        max_len: Optional[int] = None, **kw) -> "StarVectorForCausalLM":
+        """Load a LOCAL checkpoint directory (config.json + *.safetensors / pytorch_model.bin).  No hub access."""
+        config = StarVectorConfig.from_pretrained(path)
+        sd: Dict[str, torch.Tensor] = {}
+        files = sorted(f for f in os.listdir(path) if f.endswith(".safetensors"))
+        if files:
+            from safetensors.torch import load_file
+
+            for f in files:
+                sd.update(load_file(os.path.join(path, f)))
+        elif os.path.exists(os.path.join(path, "pytorch_model.bin")):
+            sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+        else:
+            raise FileNotFoundError(f"no *.safetensors / pytorch_model.bin under {path}")
+        return cls(config, sd, device=device, max_batch=max_batch, max_len=max_len, tokenizer_path=path)
+
+    def save_pretrained(self, path: str, state_dict: Dict[str, torch.Tensor]) -> None:
+        from safetensors.torch import save_file
+
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, "config.json"), "w") as f:
+            json.dump(self.config.to_dict(), f, indent=1)
+        save_file({k: v.contiguous() for k, v in state_dict.items() if not k.endswith("lm_head.weight")},
+                  os.path.join(path, "model.safetensors"))
+
+    # -- nn.Module-ish no-ops the callers use (quickstart.py:11-12) ------------------------
+    def cuda(self, *a, **k): return self
+    def to(self, *a, **k): return self
+    def eval(self): return self
+    def half(self): return self
+    def bfloat16(self): return self
+
+    # -- the surface ---------------------------------------------------------------------
+    def generate_im2svg(self, batch, **kwargs) -> List[str]:                  # starvector_arch.py:186-187
+        return self.model.generate_im2svg(batch, **kwargs)
+
+    def generate_im2text(self, batch, **kwargs):                              # :189-190 (dangling in the reference too)
+        raise AttributeError("generate_im2text has no implementation in the reference model core either")
+
+    def process_images(self, images):                                         # :192-193
+        return self.model.image_encoder.process_images(images)

@@ -1,0 +1,108 @@
+"""CPU tests of the host side: ABI surface, config/tokenizer/params plumbing, loud failure without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from starvector_b200 import _lib
+from starvector_b200.config import StarVectorConfig, dims_1b, dims_tiny
+from starvector_b200.engine import GenerationParams
+from starvector_b200.tokenizer import SyntheticTokenizer
+from starvector_b200.weights import synthetic_state_dict, weight_shapes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "starvector_b200.h")).read()
+    return set(re.findall(r"SV_API\s+[\w\s\*]+?\b(sv_\w+)\s*\(", text))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert declared, "no SV_API declarations parsed"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (sv_\w+)", out))
+    assert declared == exported, (declared ^ exported)
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert lib.sv_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(_lib.ModelDesc) == 19 * 4
+    assert C.sizeof(_lib.GenParams) == 88 and _lib.GenParams.seed.offset == 72
+
+
+def test_create_rejects_bad_descriptors_without_touching_cuda():
+    lib = _lib.load()
+    h = C.c_void_p()
+    d = _lib.ModelDesc(variant=1)
+    assert lib.sv_engine_create(C.byref(d), 0, C.byref(h)) == _lib.SV_ERR_UNSUPPORTED
+    assert b"StarCoder2" in lib.sv_last_error(None)
+    d = _lib.ModelDesc(vit_width=100, vit_heads=2)
+    assert lib.sv_engine_create(C.byref(d), 0, C.byref(h)) == _lib.SV_ERR_INVALID
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_engine_fails_loudly_without_gpu():
+    from starvector_b200.engine import Engine
+
+    with pytest.raises(_lib.EngineError, match="no CPU fallback"):
+        Engine(dims_tiny())
+    lib = _lib.load()
+    h = C.c_void_p()
+    t = dims_tiny()
+    d = _lib.ModelDesc(image_size=t.image_size, patch_size=t.patch_size, vit_width=t.vit_width, vit_layers=1,
+                       vit_heads=t.vit_heads, vit_mlp=t.vit_mlp, hidden=t.hidden, n_layer=1, n_head=t.n_head,
+                       n_kv_head=1, head_dim=128, n_inner=t.n_inner, n_positions=64, vocab=500, ln_eps=1e-5,
+                       max_batch=1, max_len=64)
+    assert lib.sv_engine_create(C.byref(d), 0, C.byref(h)) == _lib.SV_ERR_CUDA
+    assert b"no CPU fallback" in lib.sv_last_error(None)
+
+
+def test_1b_dimensions_match_survey():
+    d = dims_1b()
+    assert d.query_length == 257 and d.patch_k == 588 and d.patch_k_padded == 640
+    assert d.decoder_weight_bytes() == 2_240_876_544          # SURVEY.md §8d `W`
+    assert d.kv_bytes_per_token() == 12_288
+    n = sum(int(torch.tensor(s).prod()) for _, s, _ in weight_shapes(d))
+    assert 1.42e9 < n < 1.45e9                                  # ViT 290.6M + adapter ~7.3M(+norm) + decoder 1137M
+
+
+def test_config_roundtrip_and_dims():
+    c = StarVectorConfig()
+    d = c.to_dims(max_batch=2, max_len=4096)
+    assert (d.hidden, d.n_layer, d.vocab, d.max_len) == (2048, 24, 49156, 4096)
+    with pytest.raises(NotImplementedError):
+        StarVectorConfig(starcoder_model_name="bigcode/starcoder2-7b").to_dims()
+    c2 = StarVectorConfig(**{k: v for k, v in c.to_dict().items() if k not in ("model_type", "_name_or_path")})
+    assert c2.hidden_size == c.hidden_size
+
+
+def test_synthetic_tokenizer_roundtrip():
+    t = SyntheticTokenizer(49156)
+    assert t("<svg", add_special_tokens=False)["input_ids"] == [44, 5678]
+    assert t.pad_token_id == 49152 and t.eos_token_id == 0
+    ids = t(["<svg"] * 3, return_tensors="pt")["input_ids"]
+    assert ids.shape == (3, 2)
+    s = t.batch_decode([[44, 5678, 9, 10, 1245, 7, 29, 0, 49152]])[0]
+    assert s == "<svg<t9><t10></svg>" and t.encode(s) == [44, 5678, 9, 10, 1245, 7, 29]
+
+
+def test_generation_params_to_c():
+    p = GenerationParams(max_new_tokens=7, do_sample=True, temperature=0.8, top_p=0.9, repetition_penalty=3.1,
+                         eos_token_id=None, pad_token_id=49152, stop_ids=[1, 2, 3], seed=5).to_c()
+    assert (p.max_new_tokens, p.do_sample, p.eos_token_id, p.n_stop_ids, list(p.stop_ids)[:3]) == (7, 1, -1, 3, [1, 2, 3])
+    with pytest.raises(ValueError):
+        GenerationParams(max_new_tokens=1, stop_ids=list(range(9))).to_c()
+
+
+def test_state_dict_names_follow_reference_tree():
+    sd = synthetic_state_dict(dims_tiny(), seed=0)
+    assert "model.image_encoder.visual_encoder.transformer.resblocks.0.attn.in_proj_weight" in sd
+    assert "model.image_projection.norm.weight" in sd
+    assert sd["model.svg_transformer.transformer.lm_head.weight"] is sd["model.svg_transformer.transformer.transformer.wte.weight"]
