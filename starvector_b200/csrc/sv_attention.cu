@@ -15,18 +15,28 @@
 //   P.V   : V is kept TRANSPOSED ([dim][key]) so the "B" fragment (two consecutive keys for one
 //           dim) is contiguous; keys inside a 32-block are permuted consistently between the S
 //           accumulator columns and the V^T load: S tile j, column i  <->  key 8*(i/2) + 2j + (i%2).
+#include <algorithm>
+
 #include "sv_kernels.h"
 
 namespace sv {
 
-template <int D>
+// CG = true: L2-only loads (ld.global.cg) for data produced by the immediately preceding kernel when
+// kernels overlap under Programmatic Dependent Launch (a co-resident CTA may hold stale L1 lines).
+template <bool CG>
+SV_DEVINL uint4 ld16(const void* p) {
+  if constexpr (CG) return __ldcg(reinterpret_cast<const uint4*>(p));
+  else return ldg_cached(p);
+}
+
+template <int D, bool CG = false>
 SV_DEVINL void load_q_frag(uint32_t (&qa)[D / 16][4], const bf16* row_lo, bool ok_lo, const bf16* row_hi, bool ok_hi,
                            int t) {
 #pragma unroll
   for (int jj = 0; jj < D / 32; ++jj) {
     uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u);
-    if (ok_lo) a = ldg_cached(row_lo + 32 * jj + 8 * t);
-    if (ok_hi) b = ldg_cached(row_hi + 32 * jj + 8 * t);
+    if (ok_lo) a = ld16<CG>(row_lo + 32 * jj + 8 * t);
+    if (ok_hi) b = ld16<CG>(row_hi + 32 * jj + 8 * t);
     qa[2 * jj][0] = a.x; qa[2 * jj][1] = b.x; qa[2 * jj][2] = a.y; qa[2 * jj][3] = b.y;
     qa[2 * jj + 1][0] = a.z; qa[2 * jj + 1][1] = b.z; qa[2 * jj + 1][2] = a.w; qa[2 * jj + 1][3] = b.w;
   }
@@ -34,7 +44,7 @@ SV_DEVINL void load_q_frag(uint32_t (&qa)[D / 16][4], const bf16* row_lo, bool o
 
 // Processes keys [key_begin, key_end) (key_begin % 32 == 0).  acc/m/l are running (unnormalised)
 // output, row max (log2 domain) and per-lane partial row sums for rows g (index 0) and g+8 (1).
-template <int D>
+template <int D, bool CG = false>
 SV_DEVINL void attn_core(const uint32_t (&qa)[D / 16][4], const bf16* __restrict__ kbase, int64_t k_row_stride,
                          const bf16* __restrict__ vtbase, int64_t vt_dim_stride, int key_begin, int key_end,
                          float scale_log2, float (&acc)[D / 8][4], float (&mrow)[2], float (&lrow)[2], int lane) {
@@ -49,7 +59,7 @@ SV_DEVINL void attn_core(const uint32_t (&qa)[D / 16][4], const bf16* __restrict
       const bf16* kp = kbase + (int64_t)key * k_row_stride + 8 * t;
 #pragma unroll
       for (int jj = 0; jj < D / 32; ++jj) {
-        const uint4 w = ldg_cached(kp + 32 * jj);
+        const uint4 w = ld16<CG>(kp + 32 * jj);
         mma_bf16_16816(s[j], qa[2 * jj][0], qa[2 * jj][1], qa[2 * jj][2], qa[2 * jj][3], w.x, w.y);
         mma_bf16_16816(s[j], qa[2 * jj + 1][0], qa[2 * jj + 1][1], qa[2 * jj + 1][2], qa[2 * jj + 1][3], w.z, w.w);
       }
@@ -92,7 +102,7 @@ SV_DEVINL void attn_core(const uint32_t (&qa)[D / 16][4], const bf16* __restrict
 #pragma unroll
     for (int nd = 0; nd < D / 8; ++nd) {
       acc[nd][0] *= corr0; acc[nd][1] *= corr0; acc[nd][2] *= corr1; acc[nd][3] *= corr1;
-      const uint4 w = ldg_cached(vtbase + (int64_t)(8 * nd + g) * vt_dim_stride + kb + 8 * t);
+      const uint4 w = ld16<CG>(vtbase + (int64_t)(8 * nd + g) * vt_dim_stride + kb + 8 * t);
       mma_bf16_16816(acc[nd], pa[0][0], pa[0][1], pa[0][2], pa[0][3], w.x, w.y);
       mma_bf16_16816(acc[nd], pa[1][0], pa[1][1], pa[1][2], pa[1][3], w.z, w.w);
     }
@@ -270,6 +280,119 @@ void launch_attention_decode(const bf16* qkv, int q_cols_total, const bf16* kcac
   attention_decode_merge_kernel<128><<<dim3(n_head / n_kv, n_kv, batch), 128, 0, st>>>(partial, out, state, n_head,
                                                                                       n_kv, nsplit);
   count_launch(2);
+}
+
+// ------------------------------------------------------------------------------------------
+// Decode attention, fused: split-KV partials + CTA-level merge + "last CTA" final merge in ONE
+// kernel (PDL-ready).  grid = (ncta, n_kv, B), 8 warps per CTA; the CTA's key-block range is dealt
+// round-robin to its warps; warp partials meet in shared memory, CTA partials in an fp32 scratch;
+// the CTA that takes the last ticket of its (image, kv head) merges them in a fixed order.
+//   partial layout: [b][kvh][cta][ 16 (m) | 16 (l) | 16*D (acc) ]
+constexpr int kDecWarps = 8;
+template <int D>
+__global__ void __launch_bounds__(kDecWarps * 32) attention_decode_fused_kernel(
+    const bf16* __restrict__ qkv, int ld, const bf16* __restrict__ kcache, const bf16* __restrict__ vtcache,
+    float* __restrict__ partial, int* __restrict__ counters, bf16* __restrict__ out,
+    const GenState* __restrict__ state, int n_head, int n_kv, int tcap, float scale_log2) {
+  extern __shared__ float dsm[];                               // [kDecWarps][32 + 16*D]
+  __shared__ int s_last;
+  constexpr int PSZ = 32 + 16 * D;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int cta = blockIdx.x, ncta = gridDim.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int group = n_head / n_kv;
+  const int nkeys = state->cur_len + 1;                        // this token's K/V is already in the cache
+  const int blocks = (nkeys + 31) / 32;
+  const int per = (blocks + ncta - 1) / ncta;
+  const int nact = (blocks + per - 1) / per;
+  if (cta >= nact) return;
+  const int blk0 = cta * per, blk1 = min(blocks, blk0 + per);
+  const int64_t bk = (int64_t)b * n_kv + kvh;
+
+  float acc[D / 8][4], mrow[2], lrow[2];
+  attn_init<D>(acc, mrow, lrow);
+  if (blk0 + warp < blk1) {
+    const bf16* qrow = qkv + (int64_t)b * ld + (int64_t)kvh * group * D;
+    uint32_t qa[D / 16][4];
+    load_q_frag<D, true>(qa, qrow + (int64_t)g * D, g < group, qrow + (int64_t)(g + 8) * D, g + 8 < group, t);
+    for (int blk = blk0 + warp; blk < blk1; blk += kDecWarps)
+      attn_core<D, true>(qa, kcache + bk * tcap * D, D, vtcache + bk * D * tcap, tcap, blk * 32,
+                         min(nkeys, blk * 32 + 32), scale_log2, acc, mrow, lrow, lane);
+  }
+  float* ws = dsm + warp * PSZ;
+  const float l0 = quad_sum(lrow[0]), l1 = quad_sum(lrow[1]);
+  if (t == 0) { ws[g] = mrow[0]; ws[g + 8] = mrow[1]; ws[16 + g] = l0; ws[16 + g + 8] = l1; }
+#pragma unroll
+  for (int nd = 0; nd < D / 8; ++nd) {
+    *reinterpret_cast<float2*>(ws + 32 + g * D + 8 * nd + 2 * t) = make_float2(acc[nd][0], acc[nd][1]);
+    *reinterpret_cast<float2*>(ws + 32 + (g + 8) * D + 8 * nd + 2 * t) = make_float2(acc[nd][2], acc[nd][3]);
+  }
+  __syncthreads();
+  float* pg = partial + (bk * ncta + cta) * PSZ;
+  for (int idx = threadIdx.x; idx < 16 * D; idx += kDecWarps * 32) {
+    const int r = idx / D;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) M = fmaxf(M, dsm[w * PSZ + r]);
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) {
+      const float m = dsm[w * PSZ + r];
+      const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
+      L += dsm[w * PSZ + 16 + r] * sc;
+      A += dsm[w * PSZ + 32 + idx] * sc;
+    }
+    pg[32 + idx] = A;
+    if (idx % D == 0) { pg[r] = M; pg[16 + r] = L; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[bk], 1) == nact - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* p0 = partial + bk * ncta * PSZ;
+  for (int idx = threadIdx.x; idx < group * D; idx += kDecWarps * 32) {
+    const int r = idx / D;
+    float M = -INFINITY;
+    for (int c = 0; c < nact; ++c) M = fmaxf(M, __ldcg(p0 + (int64_t)c * PSZ + r));
+    float L = 0.f, A = 0.f;
+    for (int c = 0; c < nact; ++c) {
+      const float m = __ldcg(p0 + (int64_t)c * PSZ + r);
+      const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
+      L += __ldcg(p0 + (int64_t)c * PSZ + 16 + r) * sc;
+      A += __ldcg(p0 + (int64_t)c * PSZ + 32 + idx) * sc;
+    }
+    out[(int64_t)b * n_head * D + (int64_t)kvh * group * D + idx] = __float2bfloat16_rn(A / L);
+  }
+  if (threadIdx.x == 0) counters[bk] = 0;                      // re-arm for the next launch
+}
+
+int attention_decode_fused_ncta(int total_len) {
+  const int blocks = (total_len + 31) / 32;
+  return std::max(1, std::min(32, (blocks + kDecWarps - 1) / kDecWarps));
+}
+
+cudaError_t attention_decode_fused_init() {
+  return cudaFuncSetAttribute(attention_decode_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kDecWarps * (32 + 16 * 128) * (int)sizeof(float));
+}
+
+void launch_attention_decode_fused(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache,
+                                   bf16* out, float* partial, int* counters, const GenState* state, int batch,
+                                   int n_head, int n_kv, int d, int tcap, int ncta, bool pdl, cudaStream_t st) {
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)d);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ncta, n_kv, batch); cfg.blockDim = dim3(kDecWarps * 32);
+  cfg.dynamicSmemBytes = kDecWarps * (32 + 16 * 128) * sizeof(float); cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, attention_decode_fused_kernel<128>, qkv, q_cols_total, kcache, vtcache, partial, counters,
+                     out, state, n_head, n_kv, tcap, scale_log2);
+  count_launch();
 }
 
 }  // namespace sv

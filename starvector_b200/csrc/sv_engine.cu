@@ -69,7 +69,9 @@ struct sv_engine {
   float* slab_partial;
   bf16 *p_x, *p_ln, *p_qkv, *p_attn, *p_h;
   bf16 *d_x, *d_ln, *d_qkv, *d_attn, *d_h, *d_last, *logits;
-  float *logits_f32, *attn_partial;
+  float *logits_f32, *attn_partial, *amax_val;
+  int *amax_idx, *attn_counters;
+  bool fused_decode = true, use_pdl = true;
   bf16 *kcache, *vtcache;           // [layer][max_batch][n_kv][tcap][D] / [layer][max_batch][n_kv][D][tcap]
   int64_t cache_layer_stride = 0;
   GenState* state = nullptr;
@@ -214,6 +216,8 @@ bool build_buffers(sv_engine* e) {
   AL(d_x, B * H); AL(d_ln, B * H); AL(d_qkv, B * e->qkv_cols); AL(d_attn, B * H); AL(d_h, B * I); AL(d_last, B * H);
   AL(logits, B * d.vocab); AL(logits_f32, B * d.vocab);
   AL(attn_partial, B * d.n_kv_head * kMaxSplit * (32 + 16 * D));
+  AL(amax_val, (int64_t)gemv_ntiles(d.vocab) * 8); AL(amax_idx, (int64_t)gemv_ntiles(d.vocab) * 8);
+  AL(attn_counters, B * d.n_kv_head);
   e->cache_layer_stride = B * d.n_kv_head * (int64_t)e->tcap * D;
   AL(kcache, e->cache_layer_stride * d.n_layer); AL(vtcache, e->cache_layer_stride * d.n_layer);
   AL(state, 1); AL(params, 1); AL(seen, B * d.vocab); AL(next_ids, B); AL(out_ids, B * (int64_t)d.max_len);
@@ -224,6 +228,7 @@ bool build_buffers(sv_engine* e) {
   cudaMemset(e->kcache, 0, (size_t)e->cache_layer_stride * d.n_layer * sizeof(bf16));
   cudaMemset(e->vtcache, 0, (size_t)e->cache_layer_stride * d.n_layer * sizeof(bf16));
   cudaMemset(e->state, 0, sizeof(GenState));
+  cudaMemset(e->attn_counters, 0, (size_t)B * d.n_kv_head * sizeof(int));
   return cudaMallocHost(reinterpret_cast<void**>(&e->host_flag), 64) == cudaSuccess;
 }
 
@@ -326,6 +331,33 @@ int run_decode_layers(sv_engine* e, const int32_t* ids, int B, int nsplit, cudaS
   return SV_OK;
 }
 
+// Fused decode step (sv_decode_fused.cu): 5 kernels per layer + lm_head.  `ids` != nullptr embeds those
+// tokens first (teacher forcing / sampling); with nullptr, d_x was already written by select_fused.
+// Leaves bf16 logits in e->logits and per-tile argmax partials in e->amax_*.
+int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, bool pdl, cudaStream_t st) {
+  const sv_model_desc& d = e->d;
+  const int H = d.hidden, D = d.head_dim;
+  if (ids) launch_embed_tokens(ids, e->wte, e->wpe, e->state, e->d_x, B, H, d.vocab, d.n_positions, st);
+  bool first = true;
+  for (int i = 0; i < d.n_layer; ++i) {
+    const DecLayer& L = e->dec[i];
+    bf16* kc = e->kcache + e->cache_layer_stride * i;
+    bf16* vc = e->vtcache + e->cache_layer_stride * i;
+    launch_gemv8_qkv(e->d_x, L.attn_w, L.attn_b, e->d_qkv, B, e->qkv_cols, H, L.ln1_w, L.ln1_b, d.ln_eps, kc, vc,
+                     e->state, d.n_head * D, d.n_kv_head, D, e->tcap, pdl && !first, st);
+    first = false;
+    launch_attention_decode_fused(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->attn_partial, e->attn_counters,
+                                  e->state, B, d.n_head, d.n_kv_head, D, e->tcap, ncta, pdl, st);
+    launch_gemv8(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, B, H, H, SV_ACT_NONE, nullptr, nullptr, 0.f, pdl, st);
+    launch_gemv8(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, B, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b,
+                 d.ln_eps, pdl, st);
+    launch_gemv8(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, B, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0.f, pdl, st);
+  }
+  launch_gemv8_lmhead(e->d_x, e->lm_head, e->logits, B, d.vocab, H, e->lnf_w, e->lnf_b, d.ln_eps, e->amax_val,
+                      e->amax_idx, pdl, st);
+  return SV_OK;
+}
+
 int nsplit_for(const sv_engine* e, int total_len) {
   int blocks = (total_len + 31) / 32;
   return std::max(1, std::min(kMaxSplit, blocks));
@@ -414,10 +446,19 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   const char* impl = getenv("SV_LINEAR_IMPL");
   if (impl && !strcmp(impl, "rowgroup")) e->linear_impl = SV_LINEAR_ROWGROUP;
   if (impl && !strcmp(impl, "tcgen05")) e->linear_impl = SV_LINEAR_TCGEN05;
+  const char* dec = getenv("SV_DECODE");          // "legacy" = the unfused per-op kernels (A/B checks)
+  if (dec && !strcmp(dec, "legacy")) e->fused_decode = false;
+  const char* pdl = getenv("SV_PDL");             // "0" = plain stream order between decode kernels
+  if (pdl && !strcmp(pdl, "0")) e->use_pdl = false;
+  if (!gemv8_supported(d.hidden, true) || !gemv8_supported(d.n_inner, false)) e->fused_decode = false;
   if (!build_weights(e) || !build_buffers(e)) {
     std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     sv_engine_destroy(e);
     return fail(nullptr, SV_ERR_CUDA, "%s", msg.c_str());
+  }
+  if (attention_decode_fused_init() != cudaSuccess) {
+    sv_engine_destroy(e);
+    return fail(nullptr, SV_ERR_CUDA, "cannot raise the shared-memory limit of the decode attention kernel");
   }
   if (cudaStreamCreateWithFlags(&e->gen_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
@@ -561,7 +602,9 @@ int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream
   SV_CK(e, cudaSetDevice(e->device));
   LaunchScope scope(e);
   cudaStream_t st = (cudaStream_t)stream;
-  int r = run_decode_layers(e, ids, e->cur_batch, nsplit_for(e, e->host_cur_len + 1), st);
+  int r = e->fused_decode
+              ? run_decode_layers_fused(e, ids, e->cur_batch, attention_decode_fused_ncta(e->host_cur_len + 1), e->use_pdl, st)
+              : run_decode_layers(e, ids, e->cur_batch, nsplit_for(e, e->host_cur_len + 1), st);
   if (r != SV_OK) return r;
   launch_advance_len(e->state, st);
   if (logits) launch_logits_to_float(e->logits, logits, (int64_t)e->cur_batch * e->d.vocab, st);
@@ -598,29 +641,51 @@ int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t*
   SV_CK(e, cudaMemsetAsync(e->seen, 0, (size_t)B * e->d.vocab, st));
   launch_fill_i32(e->out_ids, p->pad_token_id, B * e->d.max_len, st);
 
-  // token 0 comes from the prefill logits
-  launch_select(e, B, p->do_sample, st);
-  launch_gen_finalize(e->state, e->params, B, /*advance_len=*/0, st);
+  // token 0 comes from the prefill logits.  Greedy on the fused path: one kernel selects, applies the
+  // HF stop rules and embeds the token for the first decode step.
+  const bool fused = e->fused_decode;
+  const bool fused_select = fused && !p->do_sample;
+  const int ntiles = gemv_ntiles(e->d.vocab);
+  auto select_step = [&](int advance_len, bool have_partials, bool pdl) {
+    if (fused_select) {
+      launch_select_fused(e->logits, e->d.vocab, B, have_partials ? e->amax_val : nullptr, e->amax_idx, ntiles, e->state,
+                          e->params, e->seen, e->next_ids, e->out_ids, advance_len, e->wte, e->wpe, e->d_x, e->d.hidden,
+                          e->d.n_positions, pdl, st);
+    } else {
+      launch_select(e, B, p->do_sample, st);
+      launch_gen_finalize(e->state, e->params, B, advance_len, st);
+    }
+  };
+  select_step(/*advance_len=*/0, /*have_partials=*/false, /*pdl=*/false);
 
-  const int nsplit = nsplit_for(e, e->prefix_len + max_new);
-  const long long key = (long long)B * 1000 + nsplit * 2 + (p->do_sample ? 1 : 0);
+  const int nsplit = fused ? attention_decode_fused_ncta(e->prefix_len + max_new) : nsplit_for(e, e->prefix_len + max_new);
+  const long long key = (long long)B * 100000 + nsplit * 8 + (p->do_sample ? 1 : 0) + (fused ? 2 : 0) + (e->use_pdl ? 4 : 0);
   GraphEntry& ge = e->graphs[key];
   if (!ge.exec && max_new > 1) {
-    int64_t counted = 0;
-    g_launch_counter = &counted;
-    cudaGraph_t graph = nullptr;
-    SV_CK(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int r = run_decode_layers(e, e->next_ids, B, nsplit, st);
-    launch_select(e, B, p->do_sample, st);
-    launch_gen_finalize(e->state, e->params, B, /*advance_len=*/1, st);
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    g_launch_counter = &e->launches;
-    if (r != SV_OK) { if (graph) cudaGraphDestroy(graph); return r; }
-    SV_CK(e, ce);
-    ce = cudaGraphInstantiate(&ge.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    SV_CK(e, ce);
-    ge.kernels = (int)counted;
+    for (int attempt = 0; attempt < 2 && !ge.exec; ++attempt) {
+      const bool pdl = e->use_pdl && fused && attempt == 0;
+      int64_t counted = 0;
+      g_launch_counter = &counted;
+      cudaGraph_t graph = nullptr;
+      SV_CK(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int r;
+      if (fused) r = run_decode_layers_fused(e, fused_select ? nullptr : e->next_ids, B, nsplit, pdl, st);
+      else r = run_decode_layers(e, e->next_ids, B, nsplit, st);
+      select_step(/*advance_len=*/1, /*have_partials=*/fused, pdl);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      g_launch_counter = &e->launches;
+      if (r != SV_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        ge.exec = nullptr;
+        cudaGetLastError();
+        if (!pdl) SV_CK(e, ce);          // plain capture failed: a real error
+        e->use_pdl = false;              // programmatic edges refused by this driver: plain stream order
+        continue;
+      }
+      ge.kernels = (int)counted;
+    }
   }
 
   const int poll = p->poll_interval > 0 ? p->poll_interval : 16;

