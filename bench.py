@@ -265,6 +265,7 @@ def main():
                 "h2d_bytes_per_step": int(B * 3 * d.image_size * d.image_size * 2 + B * len(PROMPT_IDS) * 4),
                 "d2h_bytes_per_step": int(B * n_new * 4 + B * 4)},
         "gpu_launches": int(launches),
+        "engine": eng.describe(),
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": "decode step (CUDA graph of the per-token kernels)",

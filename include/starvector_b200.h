@@ -145,6 +145,11 @@ SV_API int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_
 /* ---- introspection for bench/profiles ------------------------------------------------- */
 /* Kernel launches issued by this engine since creation (graph replays count their nodes). */
 SV_API int64_t sv_launch_count(const sv_engine* e);
+/* Human-readable configuration of the engine (decode mode, PDL, kernel selection) for logs/bench JSON. */
+SV_API const char* sv_engine_describe(sv_engine* e);
+/* Debug (SV_MEGA_DEBUG=1): SM-clock stamps CTA 0 took around every grid barrier of the first token of the
+ * last persistent-decode launch; n <= 1024 entries, zero-terminated. */
+SV_API int sv_debug_read_timeline(sv_engine* e, long long* out_host, int32_t n);
 /* Device time (ms) of the last sv_generate decode loop and its step count, from CUDA events
  * recorded on the launching stream. */
 SV_API int sv_last_decode_timing(const sv_engine* e, float* ms, int32_t* steps);

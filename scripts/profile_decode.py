@@ -28,4 +28,20 @@ for rep in range(a.reps):
     torch.cuda.synchronize()
     ms, steps = eng.last_decode_timing()
     print(f"rep {rep}: {steps} decode steps in {ms:.3f} ms -> {ms / max(steps, 1) * 1000:.1f} us/step", flush=True)
+if os.environ.get("SV_MEGA_DEBUG"):
+    tl = eng.debug_timeline()
+    if tl:
+        t0 = tl[0]
+        names = ["qkv", "attn_part", "attn_merge", "c_proj", "fc", "proj"]
+        work = [(tl[i] - (tl[i - 1] if i else t0)) for i in range(0, len(tl), 2)]      # compute before barrier k
+        bar = [(tl[i + 1] - tl[i]) for i in range(0, len(tl) - 1, 2)]                  # time inside barrier k
+        print("stamps", len(tl), "total cycles", tl[-1] - t0)
+        for k in range(0, min(len(bar), 12)):
+            print(f"  phase {k:3d} {names[k % 6]:10s} work {work[k]:7d} cyc   barrier {bar[k]:7d} cyc")
+        per = {n: [0, 0] for n in names}
+        for k in range(min(len(bar), 144)):
+            per[names[k % 6]][0] += work[k]; per[names[k % 6]][1] += bar[k]
+        for n, (w, b) in per.items():
+            print(f"  sum over 24 layers {n:10s} work {w:9d} cyc  barrier {b:9d} cyc")
+        print("  tail (lm_head, select):", [(work[k], bar[k]) for k in range(144, len(bar))])
 eng.close()

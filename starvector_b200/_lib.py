@@ -51,6 +51,8 @@ SIGNATURES = {
     "sv_generate": (C.c_int, [_P, C.POINTER(GenParams), _P, _P, _P]),
     "sv_generate_im2svg_host": (C.c_int, [_P, _P, _I, _P, _I, C.POINTER(GenParams), _P, _P, _P]),
     "sv_launch_count": (C.c_int64, [_P]),
+    "sv_engine_describe": (C.c_char_p, [_P]),
+    "sv_debug_read_timeline": (C.c_int, [_P, C.POINTER(C.c_longlong), _I]),
     "sv_last_decode_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "sv_op_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "sv_op_linear": (C.c_int, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -25,6 +25,7 @@
 // L2-only loads (ld.global.cg), because a co-resident CTA of the previous kernel may have left a
 // stale copy of an in-place-updated buffer in this SM's L1.
 #include "sv_kernels.h"
+#include "sv_select.cuh"
 
 namespace sv {
 
@@ -306,9 +307,6 @@ void launch_gemv8_lmhead(const bf16* x, const bf16* w, bf16* logits, int B, int 
 // Token selection + HF stop bookkeeping + next-token embedding in ONE single-CTA kernel.
 // Greedy without a repetition penalty reduces the lm_head's per-tile argmax partials; otherwise the
 // full bf16 logits row is scanned (penalty changes the order).  Semantics: SURVEY.md App. B.3-6.
-struct AmaxPair { float v; int i; };
-SV_DEVINL AmaxPair amax_better(AmaxPair a, AmaxPair b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
-
 __global__ void __launch_bounds__(1024) select_fused_kernel(const bf16* __restrict__ logits, int vocab, int batch,
                                                             const float* __restrict__ amax_val,
                                                             const int* __restrict__ amax_idx, int ntiles,
@@ -356,34 +354,7 @@ __global__ void __launch_bounds__(1024) select_fused_kernel(const bf16* __restri
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    // --- append (next*unfinished + pad*(1-unfinished)), EOS criterion, '</svg>' criterion
-    const int step = state->step;
-    for (int b = 0; b < batch; ++b) {
-      int tok = s_tok[b];
-      const bool unfinished = state->unfinished[b] != 0;
-      if (p->eos_id >= 0 && !unfinished) tok = p->pad_id;
-      int32_t* row = out_ids + (int64_t)b * p->out_stride;
-      row[step] = tok;
-      next_ids[b] = tok;
-      s_tok[b] = tok;
-      if (tok >= 0 && tok < vocab) seen[(int64_t)b * vocab + tok] = 1;
-      if (p->eos_id >= 0 && tok == p->eos_id) state->unfinished[b] = 0;
-      const int n = p->n_stop;
-      if (n > 0 && step + 1 >= n && (b == 0 || !p->stop_row0_only)) {
-        bool match = true;
-        for (int j = 0; j < n; ++j) match = match && (row[step + 1 - n + j] == p->stop_ids[j]);
-        if (match) { if (p->stop_row0_only) state->row0_stop = 1; else state->unfinished[b] = 0; }
-      }
-    }
-    // --- unfinished &= ~stop ; this_peer_finished ; advance
-    if (state->row0_stop) { for (int b = 0; b < batch; ++b) state->unfinished[b] = 0; state->row0_stop = 0; }
-    state->step = step + 1;
-    if (advance_len) state->cur_len += 1;
-    int any = 0;
-    for (int b = 0; b < batch; ++b) any |= state->unfinished[b];
-    if (!any || state->step >= p->max_new) state->done = 1;
-  }
+  if (tid == 0) select_apply_tokens(s_tok, batch, vocab, state, p, seen, next_ids, out_ids, advance_len);
   __syncthreads();
   // --- next step's input: wte[token] + wpe[position] (bf16 add), GPTBigCodeModel.forward
   int pos = state->cur_len;

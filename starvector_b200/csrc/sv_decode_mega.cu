@@ -1,0 +1,714 @@
+// Persistent decode kernel: `nsteps` whole tokens (all layers, lm_head, token selection) in ONE
+// cooperative launch, one CTA per SM.  This is the B=1..8 greedy hot loop of the BASELINE workloads.
+//
+// Why: a decode step streams 2.24 GB of weights but is cut into ~146 dependent phases of a few MB
+// each; as separate kernels every phase pays launch ramp + drain (measured: 122 launches/step,
+// ~25% of the HBM roofline).  Here the phase boundaries are grid barriers that only the compute
+// warps take, while a dedicated producer warp keeps streaming weights through them:
+//
+//   warp 8 (producer, one elected lane): walks the STATIC weight schedule of the whole launch
+//       (layer 0 c_attn tiles, c_proj, c_fc, mlp.c_proj, layer 1 ..., lm_head, next token ...) and
+//       copies [R rows x 1024 k] weight slabs into a 5-slot shared-memory ring with
+//       cp.async.bulk (TMA bulk copy, one instruction per 2 KB row segment, completion on the
+//       slot's "full" mbarrier).  It never waits for activations, so ~165 KB per SM (24 MB chip
+//       wide) of HBM reads stay in flight across barriers, LayerNorm prologues and attention.
+//   warps 0-7 (consumers): wait on "full", read 128-bit MMA fragments from the slot (row pitch
+//       = 2 KB + 64 B, bank-conflict free), multiply with register-resident activation fragments
+//       (mma.sync m16n8k16, weights = A, the <= 8 image rows = B), release the slot ("empty"
+//       mbarrier, one arrive per warp), and at tile end do the deterministic cross-warp split-K
+//       reduction + the reference's bf16 epilogue (bias, gelu, residual, KV-cache append, argmax).
+//   Attention (split-KV, MQA: the 16 query heads are the MMA M dimension) reads K / V^T with
+//       L2-only loads; CTA-level partials are merged by a second short phase.
+//
+// Work split: N output rows are tiled R <= 16 rows at a time so that every CTA owns the same
+// number of rows (2048 -> 147 x 14, 2304 -> 144 x 16, 8192 -> 147 x 4 x 14, 49156 -> 147 x 21 x 16).
+// All cross-CTA data (activations, partials, state) is written with plain stores and read with
+// ld.global.cg after a release/acquire grid barrier; weights use the async proxy only.
+// Every wait (mbarrier, grid barrier) is bounded and traps instead of hanging the GPU.
+#include <cstdio>
+
+#include "sv_kernels.h"
+#include "sv_select.cuh"
+
+namespace sv {
+namespace mega {
+
+constexpr int NWC = 8;                               // consumer warps
+constexpr int NCT = NWC * 32;                        // consumer threads
+constexpr int NTHREADS = NCT + 32;                   // + producer warp
+constexpr int KS_MAX = 1024;                         // k elements per ring slot row
+constexpr int SLOT_BYTES = 16 * (KS_MAX * 2 + 64);   // 16 rows x (2 KB + 64 B pad)
+constexpr int STAGES = 5;
+constexpr int D = 128;
+constexpr int PSZ = 32 + 16 * D;                     // floats per attention partial: m[16] l[16] acc[16][D]
+constexpr int ATT_BYTES = 4 * PSZ * 4;               // tree-merge buffer: 4 warp partials
+constexpr int RED_BYTES = 2 * NWC * 16 * 8 * 4;
+constexpr int OFF_ATT = STAGES * SLOT_BYTES;
+constexpr int OFF_RED = OFF_ATT + ATT_BYTES;
+constexpr int OFF_STAT = OFF_RED + RED_BYTES;
+constexpr int OFF_BAR = OFF_STAT + NWC * 8 * 4;
+constexpr int OFF_TOK = OFF_BAR + 2 * STAGES * 8;
+constexpr int SMEM_BYTES = OFF_TOK + 64 + 128;       // + alignment slack
+
+SV_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SV_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+SV_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+SV_DEVINL void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+SV_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0;; ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if (it > (1u << 22)) __trap();
+  }
+}
+SV_DEVINL void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+SV_DEVINL uint4 lds16(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+SV_DEVINL void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
+SV_DEVINL uint4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+
+using Layer = MegaLayer;
+struct Args {
+  const Layer* layers;
+  int n_layer, B, H, I, n_head, n_kv, qkv_cols, vocab, tcap, n_positions;
+  float ln_eps;
+  const bf16 *wte, *wpe, *lnf_w, *lnf_b, *lm_head;
+  bf16 *x, *qkv, *attn, *h, *logits;
+  float* attn_partial;
+  float* amax_val;
+  int* amax_idx;
+  GenState* state;
+  const GenParamsDev* params;
+  uint8_t* seen;
+  int32_t *next_ids, *out_ids;
+  unsigned int* barrier_ctr;
+  int nsteps, att_ncta;
+  long long* dbg;      // optional: CTA 0 / thread 0 clock64() stamps around every grid barrier of the first token
+};
+
+// ---- static description of one GEMV phase (identical on producer and consumers)
+struct Plan {
+  int R, tpc, ntiles, tile0, ntile, KS, nstg, pitch;
+};
+SV_DEVINL Plan make_plan(int N, int K, int cta, int ncta) {
+  Plan p;
+  const int rows_per_cta = (N + ncta - 1) / ncta;
+  p.tpc = (rows_per_cta + 15) / 16;
+  p.R = (rows_per_cta + p.tpc - 1) / p.tpc;
+  p.ntiles = (N + p.R - 1) / p.R;
+  p.tile0 = cta * p.tpc;
+  p.ntile = max(0, min(p.tpc, p.ntiles - p.tile0));
+  p.KS = K < KS_MAX ? K : KS_MAX;
+  p.nstg = K / p.KS;
+  p.pitch = p.KS * 2 + 64;
+  return p;
+}
+
+struct Ring {
+  uint32_t base, full0, empty0;      // shared addresses
+  uint32_t slot, phase;
+  SV_DEVINL void advance() { if (++slot == STAGES) { slot = 0; phase ^= 1u; } }
+};
+
+// ---- producer warp: stream one phase's weight slabs for this CTA.  Lane 0 arms the slot's "full"
+// barrier, then lane i issues the bulk copy of row i (16 copies in flight per slot, issued in parallel).
+SV_DEVINL void produce_phase(Ring& r, const bf16* W, int N, int K, int cta, int ncta, int lane) {
+  const Plan p = make_plan(N, K, cta, ncta);
+  for (int tl = 0; tl < p.ntile; ++tl) {
+    const int row0 = (p.tile0 + tl) * p.R;
+    const int rows = min(p.R, N - row0);
+    for (int ks = 0; ks < p.nstg; ++ks) {
+      const uint32_t fb = r.full0 + 8u * r.slot;
+      if (lane == 0) {
+        mbar_wait(r.empty0 + 8u * r.slot, r.phase ^ 1u);
+        mbar_expect_tx(fb, (uint32_t)(rows * p.KS * 2));
+      }
+      __syncwarp();
+      if (lane < rows)
+        bulk_g2s(r.base + r.slot * SLOT_BYTES + lane * p.pitch, W + (int64_t)(row0 + lane) * K + (int64_t)ks * p.KS,
+                 (uint32_t)(p.KS * 2), fb);
+      r.advance();
+    }
+  }
+}
+
+// ---- grid barrier among the consumer threads of all CTAs (monotonic counter, wrap-safe compare)
+SV_DEVINL void grid_barrier(unsigned int* ctr, unsigned int& target, int ncta) {
+  target += (unsigned int)ncta;
+  consumer_sync();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    unsigned int v;
+    for (uint32_t it = 0;; ++it) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (it > (1u << 24)) __trap();
+    }
+    __threadfence();
+  }
+  consumer_sync();
+}
+
+enum { EPI_PLAIN = 0, EPI_QKV = 1, EPI_LMHEAD = 2 };
+
+struct Ctx {
+  const Args* a;
+  uint8_t* smem;
+  int cta, ncta, warp, lane, g, t;
+  float* red;     // [2][NWC][16][8]
+  float* stat;    // [NWC][8]
+};
+
+// ---- consumer: one GEMV phase  Y[B,N] = epi( LN?(X)[B,K] . W[N,K]^T )
+template <bool HAS_LN, int EPI>
+SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, const bf16* __restrict__ bias,
+                          const bf16* res, bf16* Y, int N, int K, int act, const bf16* __restrict__ ln_w,
+                          const bf16* __restrict__ ln_b, const Layer* L) {
+  const Args& a = *cx.a;
+  const Plan p = make_plan(N, K, cx.cta, cx.ncta);
+  const int warp = cx.warp, g = cx.g, t = cx.t;
+  const int cps = p.KS >> 5;                         // 32-wide chunks per slot row
+  const int cpws = (cps + NWC - 1) / NWC;            // chunks per warp per slot (<= 4)
+  const bool row_ok = g < a.B;
+  const bf16* xp = X + (int64_t)(row_ok ? g : 0) * K + 8 * t;
+  const bool big_k = p.nstg > 2;
+
+  // activations for the whole phase live in registers when K <= 2048 (8 fragments per lane)
+  uint4 xr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xr[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (!big_k && p.ntile > 0) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cl = warp + NWC * j;
+        const bool okc = ks < p.nstg && j < cpws && cl < cps;
+        if (okc && row_ok) xr[ks * 4 + j] = ldcg16(xp + (ks * cps + cl) * 32);
+      }
+    }
+    if constexpr (HAS_LN) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float f[8];
+        unpack8(xr[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+      }
+      s = quad_sum(s);
+      if (t == 0) cx.stat[warp * 8 + g] = s;
+      consumer_sync();
+      float mean = 0.f;
+#pragma unroll
+      for (int w = 0; w < NWC; ++w) mean += cx.stat[w * 8 + g];
+      mean /= (float)K;
+      float q = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool okc = ks < p.nstg && j < cpws && (warp + NWC * j) < cps;
+          if (okc) {
+            float f[8];
+            unpack8(xr[ks * 4 + j], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float dlt = f[e] - mean; q += dlt * dlt; }
+          }
+        }
+      }
+      q = quad_sum(q);
+      consumer_sync();
+      if (t == 0) cx.stat[warp * 8 + g] = q;
+      consumer_sync();
+      float var = 0.f;
+#pragma unroll
+      for (int w = 0; w < NWC; ++w) var += cx.stat[w * 8 + g];
+      const float rstd = 1.0f / sqrtf(var / (float)K + a.ln_eps);
+      // (the weight ring keeps HBM busy on its own, so the LN affine is fetched late to save registers)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cl = warp + NWC * j;
+          const bool okc = ks < p.nstg && j < cpws && cl < cps;
+          float f[8], wf[8], bfv[8];
+          unpack8(xr[ks * 4 + j], f);
+          const int ch = okc ? ks * cps + cl : 0;
+          unpack8(ldg_cached(ln_w + ch * 32 + 8 * t), wf);
+          unpack8(ldg_cached(ln_b + ch * 32 + 8 * t), bfv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = (row_ok && okc) ? (f[e] - mean) * rstd * wf[e] + bfv[e] : 0.f;
+          xr[ks * 4 + j] = pack8(f);       // ln output is a bf16 tensor in the reference; 0 on padded chunks
+        }
+      }
+    }
+  }
+
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tl = 0; tl < p.ntile; ++tl) {
+    const int tile = p.tile0 + tl;
+    if (!big_k) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        if (ks < p.nstg) {
+          mbar_wait(r.full0 + 8u * r.slot, r.phase);
+          const uint32_t sb = r.base + r.slot * SLOT_BYTES + g * p.pitch + t * 16;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cl = warp + NWC * j;
+            if (j < cpws && cl < cps) {
+              const uint4 lo = lds16(sb + cl * 64), hi = lds16(sb + 8 * p.pitch + cl * 64);
+              const uint4 xv = xr[ks * 4 + j];
+              mma_bf16_16816(c, lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
+              mma_bf16_16816(c, lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
+            }
+          }
+          __syncwarp();
+          if (cx.lane == 0) mbar_arrive(r.empty0 + 8u * r.slot);
+          r.advance();
+        }
+      }
+    } else {
+      // K > 2048: activation fragments are fetched per slot from L2, one slot ahead of their use
+      uint4 xc[4], xn[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cl = warp + NWC * j;
+        xc[j] = (row_ok && j < cpws && cl < cps) ? ldcg16(xp + cl * 32) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      for (int ks = 0; ks < p.nstg; ++ks) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cl = warp + NWC * j;
+          xn[j] = (row_ok && ks + 1 < p.nstg && j < cpws && cl < cps) ? ldcg16(xp + ((ks + 1) * cps + cl) * 32)
+                                                                       : make_uint4(0u, 0u, 0u, 0u);
+        }
+        mbar_wait(r.full0 + 8u * r.slot, r.phase);
+        const uint32_t sb = r.base + r.slot * SLOT_BYTES + g * p.pitch + t * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cl = warp + NWC * j;
+          if (j < cpws && cl < cps) {
+            const uint4 lo = lds16(sb + cl * 64), hi = lds16(sb + 8 * p.pitch + cl * 64);
+            mma_bf16_16816(c, lo.x, hi.x, lo.y, hi.y, xc[j].x, xc[j].y);
+            mma_bf16_16816(c, lo.z, hi.z, lo.w, hi.w, xc[j].z, xc[j].w);
+          }
+        }
+        __syncwarp();
+        if (cx.lane == 0) mbar_arrive(r.empty0 + 8u * r.slot);
+        r.advance();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xc[j] = xn[j];
+      }
+    }
+    // ---- tile finished: deterministic cross-warp split-K reduction + epilogue
+    float* rd = cx.red + (tl & 1) * (NWC * 16 * 8);
+    rd[(warp * 16 + g) * 8 + 2 * t] = c[0]; rd[(warp * 16 + g) * 8 + 2 * t + 1] = c[1];
+    rd[(warp * 16 + g + 8) * 8 + 2 * t] = c[2]; rd[(warp * 16 + g + 8) * 8 + 2 * t + 1] = c[3];
+    c[0] = c[1] = c[2] = c[3] = 0.f;
+    consumer_sync();
+    if (threadIdx.x < 128) {
+      const int n = threadIdx.x & 15, mm = threadIdx.x >> 4;
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < NWC; ++w) acc += rd[(w * 16 + n) * 8 + mm];
+      const int col = tile * p.R + n;
+      const bool ok = n < p.R && col < N && mm < a.B;
+      float v = 0.f;
+      if (ok) {
+        const float bv = bias ? __bfloat162float(bias[col]) : 0.f;
+        float rv = 0.f;
+        if (res) rv = __bfloat162float(__ldcg(res + (int64_t)mm * N + col));
+        v = epilogue_elem(acc, bv, act, res != nullptr, rv);
+        const bf16 vb = __float2bfloat16_rn(v);
+        Y[(int64_t)mm * N + col] = vb;
+        if constexpr (EPI == EPI_QKV) {
+          const int q_cols = a.n_head * D, j = col - q_cols;
+          const int pos = __ldcg(&a.state->cur_len);
+          if (j >= 0 && pos < a.tcap) {
+            if (j < a.n_kv * D) {
+              const int kvh = j / D, dim = j % D;
+              L->kc[(((int64_t)mm * a.n_kv + kvh) * a.tcap + pos) * D + dim] = vb;
+            } else {
+              const int jj = j - a.n_kv * D, kvh = jj / D, dim = jj % D;
+              L->vc[(((int64_t)mm * a.n_kv + kvh) * D + dim) * a.tcap + pos] = vb;
+            }
+          }
+        }
+      }
+      if constexpr (EPI == EPI_LMHEAD) {
+        float bv = ok ? v : -INFINITY;
+        int bi = ok ? col : 0x7fffffff;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (n == 0 && mm < a.B) {
+          a.amax_val[(int64_t)tile * 8 + mm] = bv;
+          a.amax_idx[(int64_t)tile * 8 + mm] = bi;
+        }
+      }
+    }
+    // red[] is double-buffered by tile parity: one barrier per tile
+  }
+}
+
+// ---- attention core on L2-only loads (same fragment walk as sv_attention.cu, see the comments there)
+SV_DEVINL void attn_block(const uint32_t (&qa)[D / 16][4], const bf16* __restrict__ kbase,
+                          const bf16* __restrict__ vtbase, int tcap, int kb, int key_end, float scale_log2,
+                          float (&acc)[D / 8][4], float (&mrow)[2], float (&lrow)[2], int g, int t) {
+  float s[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    int key = kb + 8 * (g >> 1) + 2 * j + (g & 1);
+    key = key < key_end ? key : key_end - 1;
+    const bf16* kp = kbase + (int64_t)key * D + 8 * t;
+#pragma unroll
+    for (int jj = 0; jj < D / 32; ++jj) {
+      const uint4 w = ldcg16(kp + 32 * jj);
+      mma_bf16_16816(s[j], qa[2 * jj][0], qa[2 * jj][1], qa[2 * jj][2], qa[2 * jj][3], w.x, w.y);
+      mma_bf16_16816(s[j], qa[2 * jj + 1][0], qa[2 * jj + 1][1], qa[2 * jj + 1][2], qa[2 * jj + 1][3], w.z, w.w);
+    }
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool valid = (kb + 8 * t + 2 * j + e) < key_end;
+      s[j][e] = valid ? s[j][e] * scale_log2 : -INFINITY;
+      s[j][2 + e] = valid ? s[j][2 + e] * scale_log2 : -INFINITY;
+      mx0 = fmaxf(mx0, s[j][e]);
+      mx1 = fmaxf(mx1, s[j][2 + e]);
+    }
+  }
+  mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+  const float mn0 = fmaxf(mrow[0], mx0), mn1 = fmaxf(mrow[1], mx1);
+  const float corr0 = exp2f(mrow[0] - mn0), corr1 = exp2f(mrow[1] - mn1);
+  mrow[0] = mn0; mrow[1] = mn1;
+  float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s[j][0] = exp2f(s[j][0] - mn0); s[j][1] = exp2f(s[j][1] - mn0);
+    s[j][2] = exp2f(s[j][2] - mn1); s[j][3] = exp2f(s[j][3] - mn1);
+    rs0 += s[j][0] + s[j][1]; rs1 += s[j][2] + s[j][3];
+  }
+  lrow[0] = lrow[0] * corr0 + rs0;
+  lrow[1] = lrow[1] * corr1 + rs1;
+  uint32_t pa[2][4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    pa[h][0] = pack_bf16x2(s[2 * h][0], s[2 * h][1]);
+    pa[h][1] = pack_bf16x2(s[2 * h][2], s[2 * h][3]);
+    pa[h][2] = pack_bf16x2(s[2 * h + 1][0], s[2 * h + 1][1]);
+    pa[h][3] = pack_bf16x2(s[2 * h + 1][2], s[2 * h + 1][3]);
+  }
+#pragma unroll
+  for (int nd = 0; nd < D / 8; ++nd) {
+    acc[nd][0] *= corr0; acc[nd][1] *= corr0; acc[nd][2] *= corr1; acc[nd][3] *= corr1;
+    const uint4 w = ldcg16(vtbase + (int64_t)(8 * nd + g) * tcap + kb + 8 * t);
+    mma_bf16_16816(acc[nd], pa[0][0], pa[0][1], pa[0][2], pa[0][3], w.x, w.y);
+    mma_bf16_16816(acc[nd], pa[1][0], pa[1][1], pa[1][2], pa[1][3], w.z, w.w);
+  }
+}
+
+// merge another warp's partial (in shared memory, fragment layout) into this warp's registers
+SV_DEVINL void attn_merge_from(const float* ws, float (&acc)[D / 8][4], float (&mrow)[2], float (&lq)[2], int g, int t) {
+  const float m0 = ws[g], m1 = ws[g + 8];
+  const float n0 = fmaxf(mrow[0], m0), n1 = fmaxf(mrow[1], m1);
+  const float a0 = (mrow[0] == -INFINITY) ? 0.f : exp2f(mrow[0] - n0), b0 = (m0 == -INFINITY) ? 0.f : exp2f(m0 - n0);
+  const float a1 = (mrow[1] == -INFINITY) ? 0.f : exp2f(mrow[1] - n1), b1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - n1);
+  lq[0] = lq[0] * a0 + ws[16 + g] * b0;
+  lq[1] = lq[1] * a1 + ws[16 + g + 8] * b1;
+  mrow[0] = n0; mrow[1] = n1;
+#pragma unroll
+  for (int nd = 0; nd < D / 8; ++nd) {
+    const float2 lo = *reinterpret_cast<const float2*>(ws + 32 + g * D + 8 * nd + 2 * t);
+    const float2 hi = *reinterpret_cast<const float2*>(ws + 32 + (g + 8) * D + 8 * nd + 2 * t);
+    acc[nd][0] = acc[nd][0] * a0 + lo.x * b0; acc[nd][1] = acc[nd][1] * a0 + lo.y * b0;
+    acc[nd][2] = acc[nd][2] * a1 + hi.x * b1; acc[nd][3] = acc[nd][3] * a1 + hi.y * b1;
+  }
+}
+SV_DEVINL void attn_store_to(float* ws, const float (&acc)[D / 8][4], const float (&mrow)[2], const float (&lq)[2],
+                             int g, int t) {
+  if (t == 0) { ws[g] = mrow[0]; ws[g + 8] = mrow[1]; ws[16 + g] = lq[0]; ws[16 + g + 8] = lq[1]; }
+#pragma unroll
+  for (int nd = 0; nd < D / 8; ++nd) {
+    *reinterpret_cast<float2*>(ws + 32 + g * D + 8 * nd + 2 * t) = make_float2(acc[nd][0], acc[nd][1]);
+    *reinterpret_cast<float2*>(ws + 32 + (g + 8) * D + 8 * nd + 2 * t) = make_float2(acc[nd][2], acc[nd][3]);
+  }
+}
+
+// ---- attention phase A: CTA-level partials.  item = (image, kv head, key chunk c), strided over CTAs.
+SV_DEVINL void attention_partials(const Ctx& cx, const Layer* L) {
+  const Args& a = *cx.a;
+  const int warp = cx.warp, g = cx.g, t = cx.t;
+  const int group = a.n_head / a.n_kv;
+  const int nkeys = __ldcg(&a.state->cur_len) + 1;
+  const int blocks = (nkeys + 31) / 32;
+  const int per = (blocks + a.att_ncta - 1) / a.att_ncta;
+  const int nact = (blocks + per - 1) / per;
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
+  float* att = reinterpret_cast<float*>(cx.smem + OFF_ATT);
+  const int nitems = a.B * a.n_kv * nact;
+  for (int item = cx.cta; item < nitems; item += cx.ncta) {
+    const int c = item % nact, bk = item / nact, kvh = bk % a.n_kv, b = bk / a.n_kv;
+    const int blk0 = c * per, blk1 = min(blocks, blk0 + per);
+    float acc[D / 8][4], mrow[2], lrow[2];
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
+    mrow[0] = mrow[1] = -INFINITY; lrow[0] = lrow[1] = 0.f;
+    if (blk0 + warp < blk1) {
+      const bf16* qrow = a.qkv + (int64_t)b * a.qkv_cols + (int64_t)kvh * group * D;
+      uint32_t qa[D / 16][4];
+#pragma unroll
+      for (int jj = 0; jj < D / 32; ++jj) {
+        uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
+        if (g < group) lo = ldcg16(qrow + (int64_t)g * D + 32 * jj + 8 * t);
+        if (g + 8 < group) hi = ldcg16(qrow + (int64_t)(g + 8) * D + 32 * jj + 8 * t);
+        qa[2 * jj][0] = lo.x; qa[2 * jj][1] = hi.x; qa[2 * jj][2] = lo.y; qa[2 * jj][3] = hi.y;
+        qa[2 * jj + 1][0] = lo.z; qa[2 * jj + 1][1] = hi.z; qa[2 * jj + 1][2] = lo.w; qa[2 * jj + 1][3] = hi.w;
+      }
+      const bf16* kb_ = L->kc + (int64_t)bk * a.tcap * D;
+      const bf16* vb_ = L->vc + (int64_t)bk * D * a.tcap;
+      for (int blk = blk0 + warp; blk < blk1; blk += NWC)
+        attn_block(qa, kb_, vb_, a.tcap, blk * 32, min(nkeys, blk * 32 + 32), scale_log2, acc, mrow, lrow, g, t);
+    }
+    float lq[2] = {quad_sum(lrow[0]), quad_sum(lrow[1])};
+    // tree merge 8 -> 4 -> 2 -> 1 warps through a 4-partial shared buffer
+    if (warp >= 4) attn_store_to(att + (warp - 4) * PSZ, acc, mrow, lq, g, t);
+    consumer_sync();
+    if (warp < 4) attn_merge_from(att + warp * PSZ, acc, mrow, lq, g, t);
+    consumer_sync();
+    if (warp == 2 || warp == 3) attn_store_to(att + (warp - 2) * PSZ, acc, mrow, lq, g, t);
+    consumer_sync();
+    if (warp < 2) attn_merge_from(att + warp * PSZ, acc, mrow, lq, g, t);
+    consumer_sync();
+    if (warp == 1) attn_store_to(att, acc, mrow, lq, g, t);
+    consumer_sync();
+    if (warp == 0) {
+      attn_merge_from(att, acc, mrow, lq, g, t);
+      attn_store_to(a.attn_partial + ((int64_t)bk * a.att_ncta + c) * PSZ, acc, mrow, lq, g, t);
+    }
+    consumer_sync();
+  }
+}
+
+// ---- attention phase B: merge the CTA partials, one output element per thread (all CTAs)
+SV_DEVINL void attention_merge(const Ctx& cx) {
+  const Args& a = *cx.a;
+  const int group = a.n_head / a.n_kv;
+  const int nkeys = __ldcg(&a.state->cur_len) + 1;
+  const int blocks = (nkeys + 31) / 32;
+  const int per = (blocks + a.att_ncta - 1) / a.att_ncta;
+  const int nact = (blocks + per - 1) / per;
+  const int total = a.B * a.n_head * D;
+  for (int o = cx.cta * NCT + (int)threadIdx.x; o < total; o += cx.ncta * NCT) {
+    const int dim = o % D, head = (o / D) % a.n_head, b = o / (D * a.n_head);
+    const int kvh = head / group, r = head % group;
+    const float* p0 = a.attn_partial + ((int64_t)(b * a.n_kv + kvh) * a.att_ncta) * PSZ;
+    float M = -INFINITY;
+    for (int c = 0; c < nact; ++c) M = fmaxf(M, __ldcg(p0 + (int64_t)c * PSZ + r));
+    float Lsum = 0.f, A = 0.f;
+    for (int c = 0; c < nact; ++c) {
+      const float m = __ldcg(p0 + (int64_t)c * PSZ + r);
+      const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
+      Lsum += __ldcg(p0 + (int64_t)c * PSZ + 16 + r) * sc;
+      A += __ldcg(p0 + (int64_t)c * PSZ + 32 + r * D + dim) * sc;
+    }
+    a.attn[(int64_t)b * a.n_head * D + head * D + dim] = __float2bfloat16_rn(A / Lsum);
+  }
+}
+
+// ---- token selection (CTA 0): argmax partials (or penalised full scan) -> HF bookkeeping -> embedding
+SV_DEVINL void select_phase(const Ctx& cx, int ntiles) {
+  const Args& a = *cx.a;
+  if (cx.cta != 0) return;
+  if (__ldcg(&a.state->done)) return;
+  AmaxPair* sm = reinterpret_cast<AmaxPair*>(cx.red);
+  int* s_tok = reinterpret_cast<int*>(cx.smem + OFF_TOK);
+  const int tid = threadIdx.x;
+  const float rp = a.params->rep_penalty;
+  for (int b = 0; b < a.B; ++b) {
+    AmaxPair best{-INFINITY, 0x7fffffff};
+    if (rp == 1.0f) {
+      for (int i = tid; i < ntiles; i += NCT)
+        best = amax_better(best, AmaxPair{__ldcg(a.amax_val + (int64_t)i * 8 + b), __ldcg(a.amax_idx + (int64_t)i * 8 + b)});
+    } else {
+      const bf16* lr = a.logits + (int64_t)b * a.vocab;
+      const uint8_t* sr = a.seen + (int64_t)b * a.vocab;
+      for (int i = tid; i < a.vocab; i += NCT) {
+        float v = __bfloat162float(__ldcg(lr + i));
+        if (__ldcg(sr + i)) v = v < 0.f ? v * rp : v / rp;
+        best = amax_better(best, AmaxPair{v, i});
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      AmaxPair other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+      best = amax_better(best, other);
+    }
+    consumer_sync();
+    if (cx.lane == 0) sm[cx.warp] = best;
+    consumer_sync();
+    if (tid == 0) {
+      for (int w = 1; w < NWC; ++w) best = amax_better(best, sm[w]);
+      s_tok[b] = best.i == 0x7fffffff ? 0 : best.i;
+    }
+  }
+  consumer_sync();
+  if (tid == 0) {
+    select_apply_tokens(s_tok, a.B, a.vocab, a.state, a.params, a.seen, a.next_ids, a.out_ids, 1);
+    __threadfence();
+  }
+  consumer_sync();
+  int pos = a.state->cur_len;        // written by this CTA's thread 0 just above (same-CTA visibility after bar)
+  pos = pos >= a.n_positions ? a.n_positions - 1 : pos;
+  const int hv = a.H >> 3;
+  for (int i = tid; i < a.B * hv; i += NCT) {
+    const int b = i / hv, col = (i % hv) * 8;
+    int id = s_tok[b];
+    id = id < 0 ? 0 : (id >= a.vocab ? a.vocab - 1 : id);
+    float e[8], q[8];
+    unpack8(ldg_cached(a.wte + (int64_t)id * a.H + col), e);
+    unpack8(ldg_cached(a.wpe + (int64_t)pos * a.H + col), q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] += q[j];
+    *reinterpret_cast<uint4*>(a.x + (int64_t)b * a.H + col) = pack8(e);
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) decode_mega_kernel(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  Ring ring;
+  ring.base = smem_u32(smem);
+  ring.full0 = smem_u32(smem + OFF_BAR);
+  ring.empty0 = ring.full0 + 8u * STAGES;
+  ring.slot = 0; ring.phase = 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(ring.full0 + 8u * s, 1); mbar_init(ring.empty0 + 8u * s, NWC); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int qkv_n = a.qkv_cols;
+  if (warp == NWC) {
+    // =========================== producer ===========================
+    for (int s = 0; s < a.nsteps; ++s) {
+      for (int l = 0; l < a.n_layer; ++l) {
+        const Layer* L = a.layers + l;
+        produce_phase(ring, L->attn_w, qkv_n, a.H, cta, ncta, lane);
+        produce_phase(ring, L->proj_w, a.H, a.H, cta, ncta, lane);
+        produce_phase(ring, L->fc_w, a.I, a.H, cta, ncta, lane);
+        produce_phase(ring, L->fc2_w, a.H, a.I, cta, ncta, lane);
+      }
+      produce_phase(ring, a.lm_head, a.vocab, a.H, cta, ncta, lane);
+    }
+    return;   // in-flight bulk copies are all consumed (and thus complete) before the consumers exit
+  }
+  // =========================== consumers ===========================
+  Ctx cx;
+  cx.a = &a; cx.smem = smem; cx.cta = cta; cx.ncta = ncta; cx.warp = warp; cx.lane = lane; cx.g = lane >> 2; cx.t = lane & 3;
+  cx.red = reinterpret_cast<float*>(smem + OFF_RED);
+  cx.stat = reinterpret_cast<float*>(smem + OFF_STAT);
+  unsigned int target = 0;
+  const int ntiles_lm = make_plan(a.vocab, a.H, 0, ncta).ntiles;
+  int dbg_i = 0;
+  const bool dbg_on = a.dbg != nullptr && cta == 0 && threadIdx.x == 0;
+#define SV_STAMP() do { if (dbg_on && s == 0 && dbg_i < 1000) a.dbg[dbg_i++] = clock64(); } while (0)
+#define SV_GRID_BARRIER() do { SV_STAMP(); grid_barrier(a.barrier_ctr, target, ncta); SV_STAMP(); } while (0)
+  for (int s = 0; s < a.nsteps; ++s) {
+    for (int l = 0; l < a.n_layer; ++l) {
+      const Layer* L = a.layers + l;
+      gemv_phase<true, EPI_QKV>(cx, ring, a.x, L->attn_b, nullptr, a.qkv, qkv_n, a.H, 0, L->ln1_w, L->ln1_b, L);
+      SV_GRID_BARRIER();
+      attention_partials(cx, L);
+      SV_GRID_BARRIER();
+      attention_merge(cx);
+      SV_GRID_BARRIER();
+      gemv_phase<false, EPI_PLAIN>(cx, ring, a.attn, L->proj_b, a.x, a.x, a.H, a.H, 0, nullptr, nullptr, L);
+      SV_GRID_BARRIER();
+      gemv_phase<true, EPI_PLAIN>(cx, ring, a.x, L->fc_b, nullptr, a.h, a.I, a.H, 2 /*gelu_tanh*/, L->ln2_w, L->ln2_b, L);
+      SV_GRID_BARRIER();
+      gemv_phase<false, EPI_PLAIN>(cx, ring, a.h, L->fc2_b, a.x, a.x, a.H, a.I, 0, nullptr, nullptr, L);
+      SV_GRID_BARRIER();
+    }
+    gemv_phase<true, EPI_LMHEAD>(cx, ring, a.x, nullptr, nullptr, a.logits, a.vocab, a.H, 0, a.lnf_w, a.lnf_b, nullptr);
+    SV_GRID_BARRIER();
+    select_phase(cx, ntiles_lm);
+    SV_GRID_BARRIER();
+  }
+}
+
+}  // namespace mega
+
+// ---- host side
+static int g_mega_ncta = 0;
+static char g_mega_why[256] = "decode_mega_init not called";
+const char* decode_mega_status() { return g_mega_why; }
+
+cudaError_t decode_mega_init() {
+  cudaError_t e = cudaFuncSetAttribute(mega::decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       mega::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  int dev = 0, nsm = 0, per_sm = 0, coop = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega::decode_mega_kernel, mega::NTHREADS, mega::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  g_mega_ncta = (coop && per_sm >= 1) ? nsm : 0;
+  snprintf(g_mega_why, sizeof(g_mega_why), "sms=%d coop=%d blocks_per_sm=%d smem=%d threads=%d -> ncta=%d", nsm, coop,
+           per_sm, mega::SMEM_BYTES, mega::NTHREADS, g_mega_ncta);
+  return cudaSuccess;
+}
+int decode_mega_ncta() { return g_mega_ncta; }
+bool decode_mega_supported(int H, int I, int head_dim, int max_batch) {
+  auto okk = [](int K) { return K % 32 == 0 && (K <= mega::KS_MAX ? true : K % mega::KS_MAX == 0); };
+  return g_mega_ncta > 0 && head_dim == mega::D && okk(H) && okk(I) && H <= 2 * mega::KS_MAX && max_batch <= 8;
+}
+
+cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st) {
+  mega::Args a{};
+  a.layers = reinterpret_cast<const mega::Layer*>(m.layers_dev);
+  a.n_layer = m.n_layer; a.B = m.B; a.H = m.H; a.I = m.I; a.n_head = m.n_head; a.n_kv = m.n_kv; a.qkv_cols = m.qkv_cols;
+  a.vocab = m.vocab; a.tcap = m.tcap; a.n_positions = m.n_positions; a.ln_eps = m.ln_eps;
+  a.wte = m.wte; a.wpe = m.wpe; a.lnf_w = m.lnf_w; a.lnf_b = m.lnf_b; a.lm_head = m.lm_head;
+  a.x = m.x; a.qkv = m.qkv; a.attn = m.attn; a.h = m.h; a.logits = m.logits;
+  a.attn_partial = m.attn_partial; a.amax_val = m.amax_val; a.amax_idx = m.amax_idx;
+  a.state = m.state; a.params = m.params; a.seen = m.seen; a.next_ids = m.next_ids; a.out_ids = m.out_ids;
+  a.barrier_ctr = m.barrier_ctr; a.nsteps = m.nsteps; a.att_ncta = m.att_ncta; a.dbg = m.dbg;
+  cudaError_t e = cudaMemsetAsync(m.barrier_ctr, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mega::decode_mega_kernel), dim3(g_mega_ncta),
+                                  dim3(mega::NTHREADS), args, mega::SMEM_BYTES, st);
+  count_launch();
+  return e;
+}
+
+}  // namespace sv

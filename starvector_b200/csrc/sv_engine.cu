@@ -47,7 +47,7 @@ struct GraphEntry { cudaGraphExec_t exec = nullptr; int kernels = 0; };
 struct sv_engine {
   sv_model_desc d{};
   int device = 0;
-  std::string err;
+  std::string err, describe;
   int64_t launches = 0;
   int linear_impl = SV_LINEAR_AUTO;
 
@@ -71,7 +71,11 @@ struct sv_engine {
   bf16 *d_x, *d_ln, *d_qkv, *d_attn, *d_h, *d_last, *logits;
   float *logits_f32, *attn_partial, *amax_val;
   int *amax_idx, *attn_counters;
-  bool fused_decode = true, use_pdl = true;
+  bool fused_decode = true, use_pdl = true, use_mega = false;
+  MegaLayer* mega_layers = nullptr;
+  unsigned int* mega_barrier = nullptr;
+  long long* mega_dbg = nullptr;
+  bool mega_debug = false;
   bf16 *kcache, *vtcache;           // [layer][max_batch][n_kv][tcap][D] / [layer][max_batch][n_kv][D][tcap]
   int64_t cache_layer_stride = 0;
   GenState* state = nullptr;
@@ -218,6 +222,7 @@ bool build_buffers(sv_engine* e) {
   AL(attn_partial, B * d.n_kv_head * kMaxSplit * (32 + 16 * D));
   AL(amax_val, (int64_t)gemv_ntiles(d.vocab) * 8); AL(amax_idx, (int64_t)gemv_ntiles(d.vocab) * 8);
   AL(attn_counters, B * d.n_kv_head);
+  AL(mega_layers, d.n_layer); AL(mega_barrier, 4); AL(mega_dbg, 1024);
   e->cache_layer_stride = B * d.n_kv_head * (int64_t)e->tcap * D;
   AL(kcache, e->cache_layer_stride * d.n_layer); AL(vtcache, e->cache_layer_stride * d.n_layer);
   AL(state, 1); AL(params, 1); AL(seen, B * d.vocab); AL(next_ids, B); AL(out_ids, B * (int64_t)d.max_len);
@@ -451,10 +456,27 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   const char* pdl = getenv("SV_PDL");             // "0" = plain stream order between decode kernels
   if (pdl && !strcmp(pdl, "0")) e->use_pdl = false;
   if (!gemv8_supported(d.hidden, true) || !gemv8_supported(d.n_inner, false)) e->fused_decode = false;
+  const char* mg = getenv("SV_MEGA");             // "1" = persistent multi-token kernel instead of the per-phase CUDA graph
+  e->use_mega = mg && !strcmp(mg, "1");           // (opt-in until it beats the graph path: DESIGN.md "decode modes")
+  e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
   if (!build_weights(e) || !build_buffers(e)) {
     std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     sv_engine_destroy(e);
     return fail(nullptr, SV_ERR_CUDA, "%s", msg.c_str());
+  }
+  {
+    std::vector<MegaLayer> ml(d.n_layer);
+    for (int i = 0; i < d.n_layer; ++i) {
+      const DecLayer& L = e->dec[i];
+      ml[i] = MegaLayer{L.ln1_w, L.ln1_b, L.attn_w, L.attn_b, L.proj_w, L.proj_b, L.ln2_w, L.ln2_b, L.fc_w, L.fc_b,
+                        L.fc2_w, L.fc2_b, e->kcache + e->cache_layer_stride * i, e->vtcache + e->cache_layer_stride * i};
+    }
+    if (cudaMemcpy(e->mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
+        decode_mega_init() != cudaSuccess) {
+      sv_engine_destroy(e);
+      return fail(nullptr, SV_ERR_CUDA, "persistent decode kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!decode_mega_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch) || !e->fused_decode) e->use_mega = false;
   }
   if (attention_decode_fused_init() != cudaSuccess) {
     sv_engine_destroy(e);
@@ -661,7 +683,7 @@ int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t*
   const int nsplit = fused ? attention_decode_fused_ncta(e->prefix_len + max_new) : nsplit_for(e, e->prefix_len + max_new);
   const long long key = (long long)B * 100000 + nsplit * 8 + (p->do_sample ? 1 : 0) + (fused ? 2 : 0) + (e->use_pdl ? 4 : 0);
   GraphEntry& ge = e->graphs[key];
-  if (!ge.exec && max_new > 1) {
+  if (!ge.exec && max_new > 1 && !(e->use_mega && fused_select)) {
     for (int attempt = 0; attempt < 2 && !ge.exec; ++attempt) {
       const bool pdl = e->use_pdl && fused && attempt == 0;
       int64_t counted = 0;
@@ -689,14 +711,43 @@ int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t*
   }
 
   const int poll = p->poll_interval > 0 ? p->poll_interval : 16;
+  const bool can_stop = p->eos_token_id >= 0 || p->n_stop_ids > 0;
+  const bool mega = e->use_mega && fused_select;
   SV_CK(e, cudaEventRecord(e->ev_t0, st));
   int steps = 0;
   bool done = false;
-  for (int s = 1; s < max_new && !done; ++s) {
+  if (mega) {
+    // persistent kernel: up to `chunk` whole tokens per cooperative launch, no host work in between
+    const int chunk = can_stop ? poll : 256;
+    MegaLaunch m{};
+    m.layers_dev = e->mega_layers; m.n_layer = e->d.n_layer; m.B = B; m.H = e->d.hidden; m.I = e->d.n_inner;
+    m.n_head = e->d.n_head; m.n_kv = e->d.n_kv_head; m.qkv_cols = e->qkv_cols; m.vocab = e->d.vocab; m.tcap = e->tcap;
+    m.n_positions = e->d.n_positions; m.ln_eps = e->d.ln_eps; m.wte = e->wte; m.wpe = e->wpe; m.lnf_w = e->lnf_w;
+    m.lnf_b = e->lnf_b; m.lm_head = e->lm_head; m.x = e->d_x; m.qkv = e->d_qkv; m.attn = e->d_attn; m.h = e->d_h;
+    m.logits = e->logits; m.attn_partial = e->attn_partial; m.amax_val = e->amax_val; m.amax_idx = e->amax_idx;
+    m.state = e->state; m.params = e->params; m.seen = e->seen; m.next_ids = e->next_ids; m.out_ids = e->out_ids;
+    m.barrier_ctr = e->mega_barrier; m.att_ncta = nsplit;
+    m.dbg = e->mega_debug ? e->mega_dbg : nullptr;
+    if (e->mega_debug) cudaMemsetAsync(e->mega_dbg, 0, 1024 * sizeof(long long), st);
+    int left = max_new - 1;
+    while (left > 0 && !done) {
+      m.nsteps = std::min(left, chunk);
+      cudaError_t ce = launch_decode_mega(m, st);
+      if (ce != cudaSuccess) return fail(e, SV_ERR_CUDA, "persistent decode launch failed: %s", cudaGetErrorString(ce));
+      left -= m.nsteps;
+      steps += m.nsteps;
+      if (can_stop && left > 0) {
+        SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->done, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SV_CK(e, cudaStreamSynchronize(st));
+        done = e->host_flag[0] != 0;
+      }
+    }
+  }
+  for (int s = 1; s < max_new && !done && !mega; ++s) {
     SV_CK(e, cudaGraphLaunch(ge.exec, st));
     e->launches += ge.kernels;
     ++steps;
-    if ((p->eos_token_id >= 0 || p->n_stop_ids > 0) && (s % poll == 0)) {
+    if (can_stop && (s % poll == 0)) {
       SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->done, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       SV_CK(e, cudaStreamSynchronize(st));
       done = e->host_flag[0] != 0;
@@ -754,6 +805,22 @@ int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_t batch
 }
 
 int64_t sv_launch_count(const sv_engine* e) { return e ? e->launches : 0; }
+
+int sv_debug_read_timeline(sv_engine* e, long long* out_host, int32_t n) {
+  if (!e || !out_host || n < 1 || n > 1024) return SV_ERR_INVALID;
+  cudaError_t r = cudaMemcpy(out_host, e->mega_dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return r == cudaSuccess ? SV_OK : SV_ERR_CUDA;
+}
+
+const char* sv_engine_describe(sv_engine* e) {
+  if (!e) return "";
+  char buf[512];
+  snprintf(buf, sizeof(buf), "decode=%s pdl=%d linear_impl=%d mega[%s]",
+           !e->fused_decode ? "legacy-kernels" : (e->use_mega ? "persistent-kernel" : "fused-kernels-graph"),
+           (int)e->use_pdl, e->linear_impl, decode_mega_status());
+  e->describe = buf;
+  return e->describe.c_str();
+}
 
 int sv_last_decode_timing(const sv_engine* e, float* ms, int32_t* steps) {
   if (!e) return SV_ERR_INVALID;

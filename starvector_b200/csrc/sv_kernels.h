@@ -100,4 +100,32 @@ void launch_select_fused(const bf16* logits, int vocab, int batch, const float* 
                          int32_t* out_ids, int advance_len, const bf16* wte, const bf16* wpe, bf16* x, int h,
                          int n_positions, bool pdl, cudaStream_t st);
 
+// ---- sv_decode_mega.cu : persistent multi-token decode kernel (cooperative launch, one CTA per SM)
+struct MegaLayer {
+  const bf16 *ln1_w, *ln1_b, *attn_w, *attn_b, *proj_w, *proj_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *fc2_w, *fc2_b;
+  bf16 *kc, *vc;
+};
+struct MegaLaunch {
+  const MegaLayer* layers_dev;
+  int n_layer, B, H, I, n_head, n_kv, qkv_cols, vocab, tcap, n_positions;
+  float ln_eps;
+  const bf16 *wte, *wpe, *lnf_w, *lnf_b, *lm_head;
+  bf16 *x, *qkv, *attn, *h, *logits;
+  float* attn_partial;
+  float* amax_val;
+  int* amax_idx;
+  GenState* state;
+  const GenParamsDev* params;
+  uint8_t* seen;
+  int32_t *next_ids, *out_ids;
+  unsigned int* barrier_ctr;
+  int nsteps, att_ncta;
+  long long* dbg;
+};
+cudaError_t decode_mega_init();
+int decode_mega_ncta();
+const char* decode_mega_status();
+bool decode_mega_supported(int H, int I, int head_dim, int max_batch);
+cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st);
+
 }  // namespace sv

@@ -218,6 +218,14 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.sv_launch_count(self._h))
 
+    def describe(self) -> str:
+        return self._lib.sv_engine_describe(self._h).decode()
+
+    def debug_timeline(self, n: int = 1024):
+        buf = (C.c_longlong * n)()
+        self._ck(self._lib.sv_debug_read_timeline(self._h, buf, n))
+        return [int(v) for v in buf if v]
+
     def last_decode_timing(self) -> Tuple[float, int]:
         ms, steps = C.c_float(), C.c_int32()
         self._ck(self._lib.sv_last_decode_timing(self._h, C.byref(ms), C.byref(steps)))
