@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) attention_decode_fused_kernel(
   }
   __syncthreads();
   float* pg = partial + (bk * ncta + cta) * PSZ;
+  bf16* orow = out + (int64_t)b * n_head * D + (int64_t)kvh * group * D;
   for (int idx = threadIdx.x; idx < 16 * D; idx += kDecWarps * 32) {
     const int r = idx / D;
     float M = -INFINITY;
@@ -343,28 +344,69 @@ __global__ void __launch_bounds__(kDecWarps * 32) attention_decode_fused_kernel(
       L += dsm[w * PSZ + 16 + r] * sc;
       A += dsm[w * PSZ + 32 + idx] * sc;
     }
-    pg[32 + idx] = A;
-    if (idx % D == 0) { pg[r] = M; pg[16 + r] = L; }
+    if (nact == 1) {                                           // short context: this CTA saw every key
+      if (r < group) orow[idx] = __float2bfloat16_rn(A / L);
+    } else {
+      pg[32 + idx] = A;
+      if (idx % D == 0) { pg[r] = M; pg[16 + r] = L; }
+    }
   }
+  if (nact == 1) return;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&counters[bk], 1) == nact - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const float* p0 = partial + bk * ncta * PSZ;
+  // Last CTA of this (image, kv head): warp w pulls CTA partials w, w+8, ... with ONE round of independent
+  // 8-byte loads each (fragment layout), merges them in registers, and the shared-memory merge above runs again.
+  {
+    const float* p0 = partial + bk * ncta * PSZ;
+    attn_init<D>(acc, mrow, lrow);
+    float lq[2] = {0.f, 0.f};
+    for (int c = warp; c < nact; c += kDecWarps) {
+      const float* pc = p0 + (int64_t)c * PSZ;
+      const float m0 = __ldcg(pc + g), m1 = __ldcg(pc + g + 8);
+      const float pl0 = __ldcg(pc + 16 + g), pl1 = __ldcg(pc + 16 + g + 8);
+      float2 lo[D / 8], hi[D / 8];
+#pragma unroll
+      for (int nd = 0; nd < D / 8; ++nd) {
+        lo[nd] = __ldcg(reinterpret_cast<const float2*>(pc + 32 + g * D + 8 * nd + 2 * t));
+        hi[nd] = __ldcg(reinterpret_cast<const float2*>(pc + 32 + (g + 8) * D + 8 * nd + 2 * t));
+      }
+      const float n0 = fmaxf(mrow[0], m0), n1 = fmaxf(mrow[1], m1);
+      const float a0 = (mrow[0] == -INFINITY) ? 0.f : exp2f(mrow[0] - n0), b0 = (m0 == -INFINITY) ? 0.f : exp2f(m0 - n0);
+      const float a1 = (mrow[1] == -INFINITY) ? 0.f : exp2f(mrow[1] - n1), b1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - n1);
+      lq[0] = lq[0] * a0 + pl0 * b0; lq[1] = lq[1] * a1 + pl1 * b1;
+      mrow[0] = n0; mrow[1] = n1;
+#pragma unroll
+      for (int nd = 0; nd < D / 8; ++nd) {
+        acc[nd][0] = acc[nd][0] * a0 + lo[nd].x * b0; acc[nd][1] = acc[nd][1] * a0 + lo[nd].y * b0;
+        acc[nd][2] = acc[nd][2] * a1 + hi[nd].x * b1; acc[nd][3] = acc[nd][3] * a1 + hi[nd].y * b1;
+      }
+    }
+    if (t == 0) { ws[g] = mrow[0]; ws[g + 8] = mrow[1]; ws[16 + g] = lq[0]; ws[16 + g + 8] = lq[1]; }
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd) {
+      *reinterpret_cast<float2*>(ws + 32 + g * D + 8 * nd + 2 * t) = make_float2(acc[nd][0], acc[nd][1]);
+      *reinterpret_cast<float2*>(ws + 32 + (g + 8) * D + 8 * nd + 2 * t) = make_float2(acc[nd][2], acc[nd][3]);
+    }
+  }
+  __syncthreads();
   for (int idx = threadIdx.x; idx < group * D; idx += kDecWarps * 32) {
     const int r = idx / D;
     float M = -INFINITY;
-    for (int c = 0; c < nact; ++c) M = fmaxf(M, __ldcg(p0 + (int64_t)c * PSZ + r));
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) M = fmaxf(M, dsm[w * PSZ + r]);
     float L = 0.f, A = 0.f;
-    for (int c = 0; c < nact; ++c) {
-      const float m = __ldcg(p0 + (int64_t)c * PSZ + r);
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) {
+      const float m = dsm[w * PSZ + r];
       const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
-      L += __ldcg(p0 + (int64_t)c * PSZ + 16 + r) * sc;
-      A += __ldcg(p0 + (int64_t)c * PSZ + 32 + idx) * sc;
+      L += dsm[w * PSZ + 16 + r] * sc;
+      A += dsm[w * PSZ + 32 + idx] * sc;
     }
-    out[(int64_t)b * n_head * D + (int64_t)kvh * group * D + idx] = __float2bfloat16_rn(A / L);
+    orow[idx] = __float2bfloat16_rn(A / L);
   }
   if (threadIdx.x == 0) counters[bk] = 0;                      // re-arm for the next launch
 }

@@ -664,6 +664,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_mega_kernel(const Args a) 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same weight ring as ONE-PHASE kernels (per-phase CUDA-graph decode path): a producer warp
+// streams this GEMV's slabs through shared memory (starting before the PDL dependency wait, weights
+// are immutable), 8 consumer warps do LayerNorm prologue / MMA / epilogue.  ~165 KB of HBM reads
+// in flight per SM instead of the 64 KB a register-landing GEMV can hold.
+struct RingGemvArgs {
+  Args a;            // B, ln_eps, n_head, n_kv, tcap, state, amax_* (fields the epilogues read)
+  Layer L;           // kc / vc for the QKV epilogue
+  const bf16 *X, *W, *bias, *res, *ln_w, *ln_b;
+  bf16* Y;
+  int N, K, act;
+};
+
+template <bool HAS_LN, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1) gemv_ring_kernel(const RingGemvArgs ra) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  Ring ring;
+  ring.base = smem_u32(smem);
+  ring.full0 = smem_u32(smem + OFF_BAR);
+  ring.empty0 = ring.full0 + 8u * STAGES;
+  ring.slot = 0; ring.phase = 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(ring.full0 + 8u * s, 1); mbar_init(ring.empty0 + 8u * s, NWC); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp == NWC) {
+    produce_phase(ring, ra.W, ra.N, ra.K, cta, ncta, lane);     // no dependency on the previous kernel
+    return;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  Ctx cx;
+  cx.a = &ra.a; cx.smem = smem; cx.cta = cta; cx.ncta = ncta; cx.warp = warp; cx.lane = lane; cx.g = lane >> 2; cx.t = lane & 3;
+  cx.red = reinterpret_cast<float*>(smem + OFF_RED);
+  cx.stat = reinterpret_cast<float*>(smem + OFF_STAT);
+  gemv_phase<HAS_LN, EPI>(cx, ring, ra.X, ra.bias, ra.res, ra.Y, ra.N, ra.K, ra.act, ra.ln_w, ra.ln_b, &ra.L);
+}
+
 }  // namespace mega
 
 // ---- host side
@@ -709,6 +751,66 @@ cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st) {
                                   dim3(mega::NTHREADS), args, mega::SMEM_BYTES, st);
   count_launch();
   return e;
+}
+
+
+// ---- per-phase ring GEMV launchers (used by the CUDA-graph decode path)
+template <bool HAS_LN, int EPI>
+static void launch_ring_t(const mega::RingGemvArgs& ra, int ncta, bool pdl, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(mega::gemv_ring_kernel<HAS_LN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega::SMEM_BYTES);
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(mega::NTHREADS); cfg.dynamicSmemBytes = mega::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, mega::gemv_ring_kernel<HAS_LN, EPI>, ra);
+  count_launch();
+}
+
+cudaError_t gemv_ring_init() {   // set the shared-memory opt-in outside of any stream capture
+  cudaError_t e;
+#define SV_RING_ATTR(LN, EPI)                                                                                          \
+  e = cudaFuncSetAttribute(mega::gemv_ring_kernel<LN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega::SMEM_BYTES); \
+  if (e != cudaSuccess) return e;
+  SV_RING_ATTR(true, mega::EPI_QKV) SV_RING_ATTR(true, mega::EPI_PLAIN) SV_RING_ATTR(true, mega::EPI_LMHEAD)
+  SV_RING_ATTR(false, mega::EPI_PLAIN)
+#undef SV_RING_ATTR
+  return cudaSuccess;
+}
+
+bool gemv_ring_supported(int K, bool has_ln) {
+  const bool okk = K % 32 == 0 && (K <= mega::KS_MAX || K % mega::KS_MAX == 0);
+  return okk && (!has_ln || K <= 2 * mega::KS_MAX);
+}
+
+int gemv_ring_ntiles(int N) {
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int rows_per_cta = (N + nsm - 1) / nsm, tpc = (rows_per_cta + 15) / 16, R = (rows_per_cta + tpc - 1) / tpc;
+  return (N + R - 1) / R;
+}
+
+void launch_gemv_ring(const RingGemvLaunch& g, cudaStream_t st) {
+  mega::RingGemvArgs ra{};
+  ra.a.B = g.B; ra.a.ln_eps = g.ln_eps; ra.a.n_head = g.n_head; ra.a.n_kv = g.n_kv; ra.a.tcap = g.tcap; ra.a.state = const_cast<GenState*>(g.state);
+  ra.a.amax_val = g.amax_val; ra.a.amax_idx = g.amax_idx;
+  ra.L.kc = g.kcache; ra.L.vc = g.vtcache;
+  ra.X = g.X; ra.W = g.W; ra.bias = g.bias; ra.res = g.res; ra.ln_w = g.ln_w; ra.ln_b = g.ln_b; ra.Y = g.Y;
+  ra.N = g.N; ra.K = g.K; ra.act = g.act;
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const bool ln = g.ln_w != nullptr;
+  if (ln && g.epi == mega::EPI_QKV) launch_ring_t<true, mega::EPI_QKV>(ra, nsm, g.pdl, st);
+  else if (ln && g.epi == mega::EPI_LMHEAD) launch_ring_t<true, mega::EPI_LMHEAD>(ra, nsm, g.pdl, st);
+  else if (ln) launch_ring_t<true, mega::EPI_PLAIN>(ra, nsm, g.pdl, st);
+  else launch_ring_t<false, mega::EPI_PLAIN>(ra, nsm, g.pdl, st);
 }
 
 }  // namespace sv

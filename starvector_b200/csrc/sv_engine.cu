@@ -71,7 +71,7 @@ struct sv_engine {
   bf16 *d_x, *d_ln, *d_qkv, *d_attn, *d_h, *d_last, *logits;
   float *logits_f32, *attn_partial, *amax_val;
   int *amax_idx, *attn_counters;
-  bool fused_decode = true, use_pdl = true, use_mega = false;
+  bool fused_decode = true, use_pdl = true, use_mega = false, use_ring = true;
   MegaLayer* mega_layers = nullptr;
   unsigned int* mega_barrier = nullptr;
   long long* mega_dbg = nullptr;
@@ -344,6 +344,31 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
   const int H = d.hidden, D = d.head_dim;
   if (ids) launch_embed_tokens(ids, e->wte, e->wpe, e->state, e->d_x, B, H, d.vocab, d.n_positions, st);
   bool first = true;
+  if (e->use_ring) {
+    RingGemvLaunch g{};
+    g.B = B; g.ln_eps = d.ln_eps; g.n_head = d.n_head; g.n_kv = d.n_kv_head; g.tcap = e->tcap; g.state = e->state;
+    g.amax_val = e->amax_val; g.amax_idx = e->amax_idx;
+    auto gemv = [&](const bf16* X, const bf16* W, const bf16* bias, const bf16* res, bf16* Y, int N, int K, int act,
+                    const bf16* lw, const bf16* lb, int epi, bf16* kc, bf16* vc, bool p) {
+      g.X = X; g.W = W; g.bias = bias; g.res = res; g.Y = Y; g.N = N; g.K = K; g.act = act; g.ln_w = lw; g.ln_b = lb;
+      g.epi = epi; g.kcache = kc; g.vtcache = vc; g.pdl = p;
+      launch_gemv_ring(g, st);
+    };
+    for (int i = 0; i < d.n_layer; ++i) {
+      const DecLayer& L = e->dec[i];
+      bf16* kc = e->kcache + e->cache_layer_stride * i;
+      bf16* vc = e->vtcache + e->cache_layer_stride * i;
+      gemv(e->d_x, L.attn_w, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, 1, kc, vc, pdl && !first);
+      first = false;
+      launch_attention_decode_fused(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->attn_partial, e->attn_counters,
+                                    e->state, B, d.n_head, d.n_kv_head, D, e->tcap, ncta, pdl, st);
+      gemv(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, H, H, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
+      gemv(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b, 0, nullptr, nullptr, pdl);
+      gemv(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
+    }
+    gemv(e->d_x, e->lm_head, nullptr, nullptr, e->logits, d.vocab, H, SV_ACT_NONE, e->lnf_w, e->lnf_b, 2, nullptr, nullptr, pdl);
+    return SV_OK;
+  }
   for (int i = 0; i < d.n_layer; ++i) {
     const DecLayer& L = e->dec[i];
     bf16* kc = e->kcache + e->cache_layer_stride * i;
@@ -459,6 +484,9 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   const char* mg = getenv("SV_MEGA");             // "1" = persistent multi-token kernel instead of the per-phase CUDA graph
   e->use_mega = mg && !strcmp(mg, "1");           // (opt-in until it beats the graph path: DESIGN.md "decode modes")
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
+  const char* rg = getenv("SV_GEMV");             // "regs" = register-landing GEMV kernels instead of the smem weight ring
+  if (rg && !strcmp(rg, "regs")) e->use_ring = false;
+  if (!gemv_ring_supported(d.hidden, true) || !gemv_ring_supported(d.n_inner, false)) e->use_ring = false;
   if (!build_weights(e) || !build_buffers(e)) {
     std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     sv_engine_destroy(e);
@@ -472,7 +500,7 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
                         L.fc2_w, L.fc2_b, e->kcache + e->cache_layer_stride * i, e->vtcache + e->cache_layer_stride * i};
     }
     if (cudaMemcpy(e->mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
-        decode_mega_init() != cudaSuccess) {
+        decode_mega_init() != cudaSuccess || gemv_ring_init() != cudaSuccess) {
       sv_engine_destroy(e);
       return fail(nullptr, SV_ERR_CUDA, "persistent decode kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -816,7 +844,7 @@ const char* sv_engine_describe(sv_engine* e) {
   if (!e) return "";
   char buf[512];
   snprintf(buf, sizeof(buf), "decode=%s pdl=%d linear_impl=%d mega[%s]",
-           !e->fused_decode ? "legacy-kernels" : (e->use_mega ? "persistent-kernel" : "fused-kernels-graph"),
+           !e->fused_decode ? "legacy-kernels" : (e->use_mega ? "persistent-kernel" : (e->use_ring ? "ring-gemv-graph" : "reg-gemv-graph")),
            (int)e->use_pdl, e->linear_impl, decode_mega_status());
   e->describe = buf;
   return e->describe.c_str();

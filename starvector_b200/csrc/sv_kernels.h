@@ -122,6 +122,23 @@ struct MegaLaunch {
   int nsteps, att_ncta;
   long long* dbg;
 };
+// one-phase weight-ring GEMV (same device code as the persistent kernel's GEMV phases)
+struct RingGemvLaunch {
+  const bf16 *X, *W, *bias, *res, *ln_w, *ln_b;
+  bf16* Y;
+  int B, N, K, act, epi;          // epi: 0 plain, 1 QKV (+KV append), 2 lm_head (+argmax partials)
+  float ln_eps;
+  int n_head, n_kv, tcap;
+  const GenState* state;
+  bf16 *kcache, *vtcache;
+  float* amax_val;
+  int* amax_idx;
+  bool pdl;
+};
+cudaError_t gemv_ring_init();
+bool gemv_ring_supported(int K, bool has_ln);
+int gemv_ring_ntiles(int N);
+void launch_gemv_ring(const RingGemvLaunch& g, cudaStream_t st);
 cudaError_t decode_mega_init();
 int decode_mega_ncta();
 const char* decode_mega_status();
