@@ -84,8 +84,18 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_reference_run(max_new: int, threads: int, repeats: int = 1, warmup: int = 0):
-    """Time the CPU oracle (reference path restated around HF generate) on a bounded sample of the workload."""
+CPU_THREADS_CAP = 32      # decode on CPU is a GEMV stream: more threads than memory channels only adds contention
+
+
+def cpu_reference_run(threads: int, n_short: int = 4, n_long: int = 24, target_new: int = 4096, repeats: int = 1):
+    """Time the CPU oracle (the reference's generate_im2svg restated around HF generate, oracle/pipeline.py).
+
+    Bounded sample: two short greedy generations (n_short and n_long new tokens, each including ViT + adapter +
+    259-token prefill) in fp32 -- bf16 matmuls are emulated on hosts without AMX and would not finish -- from which
+    the per-token decode time and the fixed prefix time follow; the reported tokens/s is the `target_new`-token
+    workload extrapolated from those two measurements (context growth makes real long runs slightly slower, so
+    this favours the CPU).  Returns a list of dicts, one per repeat.
+    """
     from oracle.pipeline import OracleStarVector
     from starvector_b200.config import dims_1b
     from starvector_b200.weights import synthetic_images, synthetic_state_dict
@@ -93,38 +103,51 @@ def cpu_reference_run(max_new: int, threads: int, repeats: int = 1, warmup: int 
     torch.set_num_threads(threads)
     d = dims_1b(max_batch=1, max_len=8192)
     sd = synthetic_state_dict(d, seed=0)
-    o = OracleStarVector(d, sd, dtype=torch.bfloat16, eos_token_id=None, pad_token_id=49152)
+    o = OracleStarVector(d, sd, dtype=torch.float32, eos_token_id=None, pad_token_id=49152)
     del sd
-    img = synthetic_images(d, 1, seed=1)
-    kw = dict(use_nucleus_sampling=False, num_beams=1, max_length=d.query_length + len(PROMPT_IDS) + max_new)
-    times = []
-    for i in range(warmup + repeats):
+    img = synthetic_images(d, 1, seed=1).float()
+
+    def run(n):
         t0 = time.perf_counter()
-        ids = o.generate_im2svg_ids(img, PROMPT_IDS, (), **kw)
-        dt = time.perf_counter() - t0
-        assert ids.shape[1] == len(PROMPT_IDS) + max_new
-        if i >= warmup:
-            times.append(dt)
-    return times
+        ids = o.generate_im2svg_ids(img, PROMPT_IDS, (), use_nucleus_sampling=False, num_beams=1,
+                                    max_length=d.query_length + len(PROMPT_IDS) + n)
+        assert ids.shape[1] == len(PROMPT_IDS) + n
+        return time.perf_counter() - t0
+
+    run(2)                                    # untimed warm-up (allocator, oneDNN primitive caches)
+    out = []
+    for _ in range(repeats):
+        t_a, t_b = run(n_short), run(n_long)
+        if t_b <= t_a:                        # timer noise: fall back to the pessimistic-for-us bound (no prefix cost)
+            t_a = 0.0
+        per_tok = (t_b - t_a) / (n_long - n_short) if t_a else t_b / n_long
+        fixed = max(t_a - n_short * per_tok, 0.0)
+        total = fixed + target_new * per_tok
+        out.append({"seconds": t_a + t_b, "per_token_s": per_tok, "prefix_s": fixed, "tokens_per_s": target_new / total})
+    return out
+
+
+def _cpu_sample_text(n_short, n_long, target):
+    return (f"1 image, fp32, HF generate on CPU: two runs of ViT+adapter+259-token prefill+{{{n_short},{n_long}}} greedy tokens; "
+            f"tokens/s extrapolated to the {target}-token workload from the measured prefix and per-token times")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n = args.ref_new_tokens
-    times = cpu_reference_run(n, threads, repeats=args.steps, warmup=min(args.warmup, 1))
-    ms = 1000 * sum(times) / len(times)
-    v = n / (ms / 1000)
+    threads = min(os.cpu_count() or 1, CPU_THREADS_CAP)
+    runs = cpu_reference_run(threads, target_new=args.max_new_tokens, repeats=max(1, args.steps))
+    v = sum(r["tokens_per_s"] for r in runs) / len(runs)
+    ms = 1000 * sum(r["seconds"] for r in runs) / len(runs)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": len(runs),
+        "warmup": 0, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(b=1, n=args.max_new_tokens), "global_batch": 1},
         "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
-                         "sample": f"1 image, ViT+adapter+prefill+{n} greedy tokens per step (of {args.max_new_tokens}), "
-                                   "CPU oracle = reference glue restated around installed transformers GPTBigCode.generate, bf16"},
+                         "sample": _cpu_sample_text(4, 24, args.max_new_tokens),
+                         "per_token_ms": 1000 * runs[-1]["per_token_s"], "prefix_s": runs[-1]["prefix_s"]},
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -139,7 +162,6 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--max-new-tokens", type=int, default=4096)
     ap.add_argument("--batch-per-gpu", type=int, default=1)
-    ap.add_argument("--ref-new-tokens", type=int, default=32, help="bounded CPU sample (new tokens per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -272,11 +294,11 @@ def main():
                      "algorithmic_bytes_per_step": int(bytes_per_step)},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        t = cpu_reference_run(args.ref_new_tokens, threads, repeats=1, warmup=0)[0]
-        line["cpu_baseline"] = {"value": args.ref_new_tokens / t, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                "sample": f"1 image, ViT+adapter+prefill+{args.ref_new_tokens} greedy tokens "
-                                          f"(bounded sample of the {n_new}-token workload), bf16, HF generate on CPU"}
+        threads = min(os.cpu_count() or 1, CPU_THREADS_CAP)
+        r = cpu_reference_run(threads, target_new=n_new, repeats=1)[0]
+        line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": threads, "kind": "port",
+                                "sample": _cpu_sample_text(4, 24, n_new), "per_token_ms": 1000 * r["per_token_s"],
+                                "prefix_s": r["prefix_s"]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     eng.close()
