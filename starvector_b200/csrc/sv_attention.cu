@@ -437,4 +437,134 @@ void launch_attention_decode_fused(const bf16* qkv, int q_cols_total, const bf16
   count_launch();
 }
 
+// ------------------------------------------------------------------------------------------
+// Decode attention on a THREAD-BLOCK CLUSTER: the CTAs that split one image's key axis form a cluster
+// (<= 8 CTAs x 8 warps = 64 key blocks per pass) and merge their partials through DISTRIBUTED SHARED
+// MEMORY: no global scratch, no __threadfence, no atomic ticket, no second dependent trip to L2.
+//   warp partial -> own smem -> CTA partial (own smem) -> barrier.cluster -> every CTA reads all CTA
+//   partials with ld.shared::cluster for its slice of the 16x128 outputs -> bf16 store.
+SV_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+SV_DEVINL float ld_dsmem(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta_rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kDecWarps * 32, 1) attention_decode_cluster_kernel(
+    const bf16* __restrict__ qkv, int ld, const bf16* __restrict__ kcache, const bf16* __restrict__ vtcache,
+    bf16* __restrict__ out, const GenState* __restrict__ state, int n_head, int n_kv, int tcap, float scale_log2) {
+  extern __shared__ float dsm[];                               // [kDecWarps][PSZ] warp partials | [PSZ] CTA partial
+  constexpr int PSZ = 32 + 16 * D;
+  float* cta_part = dsm + kDecWarps * PSZ;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // cur_len was written by the previous token's select kernel (long complete): read it before the PDL wait
+  const int nkeys = state->cur_len + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int cta = blockIdx.x, ncta = gridDim.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int group = n_head / n_kv;
+  const int blocks = (nkeys + 31) / 32;
+  const int per = (blocks + ncta - 1) / ncta;
+  const int blk0 = cta * per, blk1 = min(blocks, blk0 + per);
+  const int64_t bk = (int64_t)b * n_kv + kvh;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  float acc[D / 8][4], mrow[2], lrow[2];
+  attn_init<D>(acc, mrow, lrow);
+  if (blk0 + warp < blk1) {
+    const bf16* qrow = qkv + (int64_t)b * ld + (int64_t)kvh * group * D;
+    uint32_t qa[D / 16][4];
+    load_q_frag<D, true>(qa, qrow + (int64_t)g * D, g < group, qrow + (int64_t)(g + 8) * D, g + 8 < group, t);
+    for (int blk = blk0 + warp; blk < blk1; blk += kDecWarps)
+      attn_core<D, true>(qa, kcache + bk * tcap * D, D, vtcache + bk * D * tcap, tcap, blk * 32,
+                         min(nkeys, blk * 32 + 32), scale_log2, acc, mrow, lrow, lane);
+  }
+  float* ws = dsm + warp * PSZ;
+  const float l0 = quad_sum(lrow[0]), l1 = quad_sum(lrow[1]);
+  if (t == 0) { ws[g] = mrow[0]; ws[g + 8] = mrow[1]; ws[16 + g] = l0; ws[16 + g + 8] = l1; }
+#pragma unroll
+  for (int nd = 0; nd < D / 8; ++nd) {
+    *reinterpret_cast<float2*>(ws + 32 + g * D + 8 * nd + 2 * t) = make_float2(acc[nd][0], acc[nd][1]);
+    *reinterpret_cast<float2*>(ws + 32 + (g + 8) * D + 8 * nd + 2 * t) = make_float2(acc[nd][2], acc[nd][3]);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 16 * D; idx += kDecWarps * 32) {      // CTA-level merge of the 8 warp partials
+    const int r = idx / D;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) M = fmaxf(M, dsm[w * PSZ + r]);
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) {
+      const float m = dsm[w * PSZ + r];
+      const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
+      L += dsm[w * PSZ + 16 + r] * sc;
+      A += dsm[w * PSZ + 32 + idx] * sc;
+    }
+    cta_part[32 + idx] = A;
+    if (idx % D == 0) { cta_part[r] = M; cta_part[16 + r] = L; }
+  }
+  cluster_sync_all();                                           // every CTA's partial is complete and visible
+  bf16* orow = out + (int64_t)b * n_head * D + (int64_t)kvh * group * D;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(cta_part);
+  for (int idx = cta * (kDecWarps * 32) + threadIdx.x; idx < group * D; idx += ncta * kDecWarps * 32) {
+    const int r = idx / D;
+    float m_c[8], l_c[8], a_c[8];
+    float M = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < ncta) {
+        m_c[c] = ld_dsmem(base + 4u * r, c);
+        l_c[c] = ld_dsmem(base + 4u * (16 + r), c);
+        a_c[c] = ld_dsmem(base + 4u * (32 + idx), c);
+        M = fmaxf(M, m_c[c]);
+      }
+    }
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < ncta) {
+        const float sc = (m_c[c] == -INFINITY) ? 0.f : exp2f(m_c[c] - M);
+        L += l_c[c] * sc;
+        A += a_c[c] * sc;
+      }
+    }
+    orow[idx] = __float2bfloat16_rn(A / L);
+  }
+  cluster_sync_all();                                           // nobody exits while its smem may still be read
+}
+
+int attention_decode_cluster_ncta(int total_len) {
+  const int blocks = (total_len + 31) / 32;
+  return std::max(1, std::min(8, (blocks + kDecWarps - 1) / kDecWarps));
+}
+
+cudaError_t attention_decode_cluster_init() {
+  return cudaFuncSetAttribute(attention_decode_cluster_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (kDecWarps + 1) * (32 + 16 * 128) * (int)sizeof(float));
+}
+
+cudaError_t launch_attention_decode_cluster(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache,
+                                            bf16* out, const GenState* state, int batch, int n_head, int n_kv, int d,
+                                            int tcap, int ncta, bool pdl, cudaStream_t st) {
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)d);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ncta, n_kv, batch); cfg.blockDim = dim3(kDecWarps * 32);
+  cfg.dynamicSmemBytes = (kDecWarps + 1) * (32 + 16 * 128) * sizeof(float); cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attention_decode_cluster_kernel<128>, qkv, q_cols_total, kcache, vtcache, out,
+                                     state, n_head, n_kv, tcap, scale_log2);
+  count_launch();
+  return e;
+}
+
 }  // namespace sv

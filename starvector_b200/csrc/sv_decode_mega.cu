@@ -26,6 +26,7 @@
 // ld.global.cg after a release/acquire grid barrier; weights use the async proxy only.
 // Every wait (mbarrier, grid barrier) is bounded and traps instead of hanging the GPU.
 #include <cstdio>
+#include <cstdlib>
 
 #include "sv_kernels.h"
 #include "sv_select.cuh"
@@ -123,8 +124,8 @@ SV_DEVINL Plan make_plan(int N, int K, int cta, int ncta) {
 
 struct Ring {
   uint32_t base, full0, empty0;      // shared addresses
-  uint32_t slot, phase;
-  SV_DEVINL void advance() { if (++slot == STAGES) { slot = 0; phase ^= 1u; } }
+  uint32_t slot, phase, nslots;
+  SV_DEVINL void advance() { if (++slot == nslots) { slot = 0; phase ^= 1u; } }
 };
 
 // ---- producer warp: stream one phase's weight slabs for this CTA.  Lane 0 arms the slot's "full"
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_mega_kernel(const Args a) 
   ring.base = smem_u32(smem);
   ring.full0 = smem_u32(smem + OFF_BAR);
   ring.empty0 = ring.full0 + 8u * STAGES;
-  ring.slot = 0; ring.phase = 0;
+  ring.slot = 0; ring.phase = 0; ring.nslots = STAGES;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(ring.full0 + 8u * s, 1); mbar_init(ring.empty0 + 8u * s, NWC); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -675,21 +676,25 @@ struct RingGemvArgs {
   const bf16 *X, *W, *bias, *res, *ln_w, *ln_b;
   bf16* Y;
   int N, K, act;
+  int nslots;        // ring depth of THIS launch: small GEMVs take 2 slots so the next kernel's CTA fits on the SM
 };
+SV_DEVINL constexpr int ring_smem_bytes(int nslots) { return nslots * SLOT_BYTES + RED_BYTES + NWC * 8 * 4 + 2 * 8 * 8 + 256; }
 
+// (A 2-CTA/SM register budget (96 regs) so that consecutive kernels co-reside under PDL was measured 25% slower.)
 template <bool HAS_LN, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemv_ring_kernel(const RingGemvArgs ra) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, ncta = gridDim.x;
+  const int off_red = ra.nslots * SLOT_BYTES, off_stat = off_red + RED_BYTES, off_bar = off_stat + NWC * 8 * 4;
   Ring ring;
   ring.base = smem_u32(smem);
-  ring.full0 = smem_u32(smem + OFF_BAR);
-  ring.empty0 = ring.full0 + 8u * STAGES;
-  ring.slot = 0; ring.phase = 0;
+  ring.full0 = smem_u32(smem + off_bar);
+  ring.empty0 = ring.full0 + 8u * 8;
+  ring.slot = 0; ring.phase = 0; ring.nslots = (uint32_t)ra.nslots;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(ring.full0 + 8u * s, 1); mbar_init(ring.empty0 + 8u * s, NWC); }
+    for (int s = 0; s < ra.nslots; ++s) { mbar_init(ring.full0 + 8u * s, 1); mbar_init(ring.empty0 + 8u * s, NWC); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -701,8 +706,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_ring_kernel(const RingGemvAr
   asm volatile("griddepcontrol.wait;" ::: "memory");
   Ctx cx;
   cx.a = &ra.a; cx.smem = smem; cx.cta = cta; cx.ncta = ncta; cx.warp = warp; cx.lane = lane; cx.g = lane >> 2; cx.t = lane & 3;
-  cx.red = reinterpret_cast<float*>(smem + OFF_RED);
-  cx.stat = reinterpret_cast<float*>(smem + OFF_STAT);
+  cx.red = reinterpret_cast<float*>(smem + off_red);
+  cx.stat = reinterpret_cast<float*>(smem + off_stat);
   gemv_phase<HAS_LN, EPI>(cx, ring, ra.X, ra.bias, ra.res, ra.Y, ra.N, ra.K, ra.act, ra.ln_w, ra.ln_b, &ra.L);
 }
 
@@ -757,13 +762,9 @@ cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st) {
 // ---- per-phase ring GEMV launchers (used by the CUDA-graph decode path)
 template <bool HAS_LN, int EPI>
 static void launch_ring_t(const mega::RingGemvArgs& ra, int ncta, bool pdl, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(mega::gemv_ring_kernel<HAS_LN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega::SMEM_BYTES);
-    attr = true;
-  }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(mega::NTHREADS); cfg.dynamicSmemBytes = mega::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(mega::NTHREADS); cfg.stream = st;
+  cfg.dynamicSmemBytes = mega::ring_smem_bytes(ra.nslots);
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -806,6 +807,14 @@ void launch_gemv_ring(const RingGemvLaunch& g, cudaStream_t st) {
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  {   // ring depth: what this CTA will stream, capped so the next kernel's CTA can co-reside (227 KB per SM)
+    static int cap = 0;
+    if (cap == 0) { const char* c = getenv("SV_RING_SLOTS"); cap = c ? atoi(c) : 5; if (cap < 1 || cap > 6) cap = 5; }
+    const int rows_per_cta = (g.N + nsm - 1) / nsm, tpc = (rows_per_cta + 15) / 16;
+    const int ks = g.K < mega::KS_MAX ? g.K : mega::KS_MAX, need = tpc * (g.K / ks);
+    ra.nslots = need < cap ? need : cap;
+    if (ra.nslots < 1) ra.nslots = 1;
+  }
   const bool ln = g.ln_w != nullptr;
   if (ln && g.epi == mega::EPI_QKV) launch_ring_t<true, mega::EPI_QKV>(ra, nsm, g.pdl, st);
   else if (ln && g.epi == mega::EPI_LMHEAD) launch_ring_t<true, mega::EPI_LMHEAD>(ra, nsm, g.pdl, st);

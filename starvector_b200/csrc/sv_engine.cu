@@ -71,7 +71,7 @@ struct sv_engine {
   bf16 *d_x, *d_ln, *d_qkv, *d_attn, *d_h, *d_last, *logits;
   float *logits_f32, *attn_partial, *amax_val;
   int *amax_idx, *attn_counters;
-  bool fused_decode = true, use_pdl = true, use_mega = false, use_ring = true;
+  bool fused_decode = true, use_pdl = true, use_mega = false, use_ring = true, use_cluster_attn = true;
   MegaLayer* mega_layers = nullptr;
   unsigned int* mega_barrier = nullptr;
   long long* mega_dbg = nullptr;
@@ -344,6 +344,14 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
   const int H = d.hidden, D = d.head_dim;
   if (ids) launch_embed_tokens(ids, e->wte, e->wpe, e->state, e->d_x, B, H, d.vocab, d.n_positions, st);
   bool first = true;
+  auto attention = [&](bf16* kc, bf16* vc) {
+    if (e->use_cluster_attn)
+      launch_attention_decode_cluster(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->state, B, d.n_head, d.n_kv_head, D,
+                                      e->tcap, std::min(ncta, 8), pdl, st);
+    else
+      launch_attention_decode_fused(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->attn_partial, e->attn_counters,
+                                    e->state, B, d.n_head, d.n_kv_head, D, e->tcap, ncta, pdl, st);
+  };
   if (e->use_ring) {
     RingGemvLaunch g{};
     g.B = B; g.ln_eps = d.ln_eps; g.n_head = d.n_head; g.n_kv = d.n_kv_head; g.tcap = e->tcap; g.state = e->state;
@@ -360,8 +368,7 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
       bf16* vc = e->vtcache + e->cache_layer_stride * i;
       gemv(e->d_x, L.attn_w, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, 1, kc, vc, pdl && !first);
       first = false;
-      launch_attention_decode_fused(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->attn_partial, e->attn_counters,
-                                    e->state, B, d.n_head, d.n_kv_head, D, e->tcap, ncta, pdl, st);
+      attention(kc, vc);
       gemv(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, H, H, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
       gemv(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b, 0, nullptr, nullptr, pdl);
       gemv(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
@@ -376,8 +383,7 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
     launch_gemv8_qkv(e->d_x, L.attn_w, L.attn_b, e->d_qkv, B, e->qkv_cols, H, L.ln1_w, L.ln1_b, d.ln_eps, kc, vc,
                      e->state, d.n_head * D, d.n_kv_head, D, e->tcap, pdl && !first, st);
     first = false;
-    launch_attention_decode_fused(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->attn_partial, e->attn_counters,
-                                  e->state, B, d.n_head, d.n_kv_head, D, e->tcap, ncta, pdl, st);
+    attention(kc, vc);
     launch_gemv8(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, B, H, H, SV_ACT_NONE, nullptr, nullptr, 0.f, pdl, st);
     launch_gemv8(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, B, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b,
                  d.ln_eps, pdl, st);
@@ -484,6 +490,8 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   const char* mg = getenv("SV_MEGA");             // "1" = persistent multi-token kernel instead of the per-phase CUDA graph
   e->use_mega = mg && !strcmp(mg, "1");           // (opt-in until it beats the graph path: DESIGN.md "decode modes")
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
+  const char* at = getenv("SV_ATTN");             // "ticket" = global-scratch + atomic-ticket merge instead of the cluster/DSMEM merge
+  if (at && !strcmp(at, "ticket")) e->use_cluster_attn = false;
   const char* rg = getenv("SV_GEMV");             // "regs" = register-landing GEMV kernels instead of the smem weight ring
   if (rg && !strcmp(rg, "regs")) e->use_ring = false;
   if (!gemv_ring_supported(d.hidden, true) || !gemv_ring_supported(d.n_inner, false)) e->use_ring = false;
@@ -506,7 +514,7 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
     }
     if (!decode_mega_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch) || !e->fused_decode) e->use_mega = false;
   }
-  if (attention_decode_fused_init() != cudaSuccess) {
+  if (attention_decode_fused_init() != cudaSuccess || attention_decode_cluster_init() != cudaSuccess) {
     sv_engine_destroy(e);
     return fail(nullptr, SV_ERR_CUDA, "cannot raise the shared-memory limit of the decode attention kernel");
   }
@@ -843,9 +851,9 @@ int sv_debug_read_timeline(sv_engine* e, long long* out_host, int32_t n) {
 const char* sv_engine_describe(sv_engine* e) {
   if (!e) return "";
   char buf[512];
-  snprintf(buf, sizeof(buf), "decode=%s pdl=%d linear_impl=%d mega[%s]",
+  snprintf(buf, sizeof(buf), "decode=%s attn=%s pdl=%d linear_impl=%d mega[%s]",
            !e->fused_decode ? "legacy-kernels" : (e->use_mega ? "persistent-kernel" : (e->use_ring ? "ring-gemv-graph" : "reg-gemv-graph")),
-           (int)e->use_pdl, e->linear_impl, decode_mega_status());
+           e->use_cluster_attn ? "cluster-dsmem" : "ticket", (int)e->use_pdl, e->linear_impl, decode_mega_status());
   e->describe = buf;
   return e->describe.c_str();
 }

@@ -293,9 +293,13 @@ bool tc05_supported(int M, int N, int K) { return M >= 1 && N >= 8 && (N % 8) ==
 cudaError_t launch_linear_tc05(const bf16* x, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int M, int N,
                                int K, int act, cudaStream_t st) {
   if (!tc05_supported(M, N, K)) return cudaErrorInvalidValue;
-  // Tile-count heuristic: 148 SMs; prefer BN=128 only when that still yields >= ~1 wave of CTAs.
+  // Tile-count heuristic for the small-M GEMMs of this path (M = 257..2072): every CTA pays ~10 us of fixed cost
+  // (launch, TMEM alloc, pipeline fill, epilogue), so never spill into a second wave if a wider tile avoids it:
+  // BN=64 while its tile count fits one wave of SMs, else BN=128.
   const int mt = (M + tc05::BM - 1) / tc05::BM;
-  const bool wide = (N % 128 == 0) && ((int64_t)mt * (N / 128) >= 120);
+  static int nsm = 0;
+  if (nsm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); if (nsm <= 0) nsm = 148; }
+  const bool wide = (N % 128 == 0) && ((int64_t)mt * ((N + 63) / 64) > nsm);
   return wide ? tc05::launch<128>(x, w, bias, res, y, M, N, K, act, st)
               : tc05::launch<64>(x, w, bias, res, y, M, N, K, act, st);
 }

@@ -85,6 +85,13 @@ void launch_attention_decode_fused(const bf16* qkv, int q_cols_total, const bf16
                                    bf16* out, float* partial, int* counters, const GenState* state, int batch,
                                    int n_head, int n_kv, int d, int tcap, int ncta, bool pdl, cudaStream_t st);
 
+// cluster / distributed-shared-memory variant (default): ncta <= 8 CTAs of one image form a cluster
+int attention_decode_cluster_ncta(int total_len);
+cudaError_t attention_decode_cluster_init();
+cudaError_t launch_attention_decode_cluster(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache,
+                                            bf16* out, const GenState* state, int batch, int n_head, int n_kv, int d,
+                                            int tcap, int ncta, bool pdl, cudaStream_t st);
+
 // ---- sv_decode_fused.cu : decode-step GEMVs with fused LayerNorm / KV append / argmax, PDL-ready
 bool gemv8_supported(int K, bool has_ln);
 int gemv_ntiles(int N);   // number of argmax partial rows the lm_head epilogue writes
