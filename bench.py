@@ -274,6 +274,12 @@ def main():
     step_ms = sum(dec_ms) / max(1, sum(dec_steps))
     achieved = bytes_per_step / (step_ms / 1000.0) / 1e9 if step_ms > 0 else 0.0
 
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_decode_step_traffic.json")
+    if os.path.exists(tpath) and B == 1:      # ncu-measured DRAM bytes of one decode step (B=1, default decode mode)
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -290,7 +296,7 @@ def main():
         "engine": eng.describe(),
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "decode step (CUDA graph of the per-token kernels)",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "decode step (CUDA graph of the per-token kernels)",
                      "algorithmic_bytes_per_step": int(bytes_per_step)},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1,6 +1,5 @@
 #!/bin/bash
-# ncu --set full captures of individual decode kernels on the per-phase (graph) path.
-#   usage: gpu_profile_kernels.sh TAG REGEX SKIP COUNT
+# ncu --set full captures of individual kernels.   usage: gpu_profile_kernels.sh TAG REGEX SKIP COUNT
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out

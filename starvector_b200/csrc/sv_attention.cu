@@ -44,13 +44,20 @@ SV_DEVINL void load_q_frag(uint32_t (&qa)[D / 16][4], const bf16* row_lo, bool o
 
 // Processes keys [key_begin, key_end) (key_begin % 32 == 0).  acc/m/l are running (unnormalised)
 // output, row max (log2 domain) and per-lane partial row sums for rows g (index 0) and g+8 (1).
-template <int D, bool CG = false>
+// HOIST_V: issue the block's V^T loads together with its K loads (one dependent memory round instead of two;
+// costs 64 more live registers, used by the latency-critical single-token decode kernel).
+template <int D, bool CG = false, bool HOIST_V = false>
 SV_DEVINL void attn_core(const uint32_t (&qa)[D / 16][4], const bf16* __restrict__ kbase, int64_t k_row_stride,
                          const bf16* __restrict__ vtbase, int64_t vt_dim_stride, int key_begin, int key_end,
                          float scale_log2, float (&acc)[D / 8][4], float (&mrow)[2], float (&lrow)[2], int lane) {
   const int g = lane >> 2, t = lane & 3;
   for (int kb = key_begin; kb < key_end; kb += 32) {
     float s[4][4];
+    uint4 vpre[HOIST_V ? D / 8 : 1];
+    if constexpr (HOIST_V) {
+#pragma unroll
+      for (int nd = 0; nd < D / 8; ++nd) vpre[nd] = ld16<CG>(vtbase + (int64_t)(8 * nd + g) * vt_dim_stride + kb + 8 * t);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
@@ -102,7 +109,9 @@ SV_DEVINL void attn_core(const uint32_t (&qa)[D / 16][4], const bf16* __restrict
 #pragma unroll
     for (int nd = 0; nd < D / 8; ++nd) {
       acc[nd][0] *= corr0; acc[nd][1] *= corr0; acc[nd][2] *= corr1; acc[nd][3] *= corr1;
-      const uint4 w = ld16<CG>(vtbase + (int64_t)(8 * nd + g) * vt_dim_stride + kb + 8 * t);
+      uint4 w;
+      if constexpr (HOIST_V) w = vpre[nd];
+      else w = ld16<CG>(vtbase + (int64_t)(8 * nd + g) * vt_dim_stride + kb + 8 * t);
       mma_bf16_16816(acc[nd], pa[0][0], pa[0][1], pa[0][2], pa[0][3], w.x, w.y);
       mma_bf16_16816(acc[nd], pa[1][0], pa[1][1], pa[1][2], pa[1][3], w.z, w.w);
     }
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 1) attention_decode_cluster_ke
     uint32_t qa[D / 16][4];
     load_q_frag<D, true>(qa, qrow + (int64_t)g * D, g < group, qrow + (int64_t)(g + 8) * D, g + 8 < group, t);
     for (int blk = blk0 + warp; blk < blk1; blk += kDecWarps)
-      attn_core<D, true>(qa, kcache + bk * tcap * D, D, vtcache + bk * D * tcap, tcap, blk * 32,
+      attn_core<D, true, true>(qa, kcache + bk * tcap * D, D, vtcache + bk * D * tcap, tcap, blk * 32,
                          min(nkeys, blk * 32 + 32), scale_log2, acc, mrow, lrow, lane);
   }
   float* ws = dsm + warp * PSZ;

@@ -676,8 +676,26 @@ struct RingGemvArgs {
   const bf16 *X, *W, *bias, *res, *ln_w, *ln_b;
   bf16* Y;
   int N, K, act;
-  int nslots;        // ring depth of THIS launch: small GEMVs take 2 slots so the next kernel's CTA fits on the SM
+  int nslots;        // ring depth of THIS launch
+  const void* next_w;            // weights the NEXT GEMV of the step will stream (immutable): prefetched into L2 here,
+  unsigned long long next_bytes; // so HBM keeps streaming across the kernel boundary / the attention kernel
 };
+
+// Each CTA asks L2 to fetch its 1/ncta share of the next weight matrix (cp.async.bulk.prefetch.L2, 4 KB pieces,
+// one per lane).  The 126 MB L2 holds the current (<= 33.5 MB) and the next (<= 33.5 MB) matrices of a layer.
+SV_DEVINL void l2_prefetch_share(const void* base, unsigned long long bytes, int cta, int ncta, int lane) {
+  if (base == nullptr || bytes == 0) return;
+  const unsigned long long per = ((bytes + ncta - 1) / ncta + 4095ull) & ~4095ull;
+  const unsigned long long lo = (unsigned long long)cta * per;
+  if (lo >= bytes) return;
+  const unsigned long long hi = lo + per < bytes ? lo + per : bytes;
+  const char* p = reinterpret_cast<const char*>(base);
+  for (unsigned long long off = lo + (unsigned long long)lane * 4096ull; off < hi; off += 32ull * 4096ull) {
+    const unsigned long long n = hi - off < 4096ull ? ((hi - off) & ~15ull) : 4096ull;
+    if (n >= 16)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"((uint32_t)n) : "memory");
+  }
+}
 SV_DEVINL constexpr int ring_smem_bytes(int nslots) { return nslots * SLOT_BYTES + RED_BYTES + NWC * 8 * 4 + 2 * 8 * 8 + 256; }
 
 // (A 2-CTA/SM register budget (96 regs) so that consecutive kernels co-reside under PDL was measured 25% slower.)
@@ -701,6 +719,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_ring_kernel(const RingGemvAr
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == NWC) {
     produce_phase(ring, ra.W, ra.N, ra.K, cta, ncta, lane);     // no dependency on the previous kernel
+    l2_prefetch_share(ra.next_w, ra.next_bytes, cta, ncta, lane);
     return;
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -804,6 +823,7 @@ void launch_gemv_ring(const RingGemvLaunch& g, cudaStream_t st) {
   ra.L.kc = g.kcache; ra.L.vc = g.vtcache;
   ra.X = g.X; ra.W = g.W; ra.bias = g.bias; ra.res = g.res; ra.ln_w = g.ln_w; ra.ln_b = g.ln_b; ra.Y = g.Y;
   ra.N = g.N; ra.K = g.K; ra.act = g.act;
+  ra.next_w = g.next_w; ra.next_bytes = g.next_bytes;
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);

@@ -71,7 +71,7 @@ struct sv_engine {
   bf16 *d_x, *d_ln, *d_qkv, *d_attn, *d_h, *d_last, *logits;
   float *logits_f32, *attn_partial, *amax_val;
   int *amax_idx, *attn_counters;
-  bool fused_decode = true, use_pdl = true, use_mega = false, use_ring = true, use_cluster_attn = true;
+  bool fused_decode = true, use_pdl = true, use_mega = false, use_ring = true, use_cluster_attn = true, use_l2_prefetch = false;
   MegaLayer* mega_layers = nullptr;
   unsigned int* mega_barrier = nullptr;
   long long* mega_dbg = nullptr;
@@ -356,24 +356,49 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
     RingGemvLaunch g{};
     g.B = B; g.ln_eps = d.ln_eps; g.n_head = d.n_head; g.n_kv = d.n_kv_head; g.tcap = e->tcap; g.state = e->state;
     g.amax_val = e->amax_val; g.amax_idx = e->amax_idx;
+    const bool l2pf = e->use_l2_prefetch;
+    static unsigned long long l2cap = 0;              // never ask for more than ~40% of the 126 MB L2
+    static int l2mask = -1;                           // which kernels prefetch: bit0 qkv, 1 c_proj, 2 fc, 3 mlp.c_proj, 4 lm_head
+    if (l2mask < 0) {
+      const char* m = getenv("SV_L2_PREFETCH_MASK"); l2mask = m ? atoi(m) : 31;
+      const char* c = getenv("SV_L2_PREFETCH_MB"); l2cap = (unsigned long long)(c ? atoi(c) : 48) << 20;
+    }
+    int which = 0;
     auto gemv = [&](const bf16* X, const bf16* W, const bf16* bias, const bf16* res, bf16* Y, int N, int K, int act,
-                    const bf16* lw, const bf16* lb, int epi, bf16* kc, bf16* vc, bool p) {
+                    const bf16* lw, const bf16* lb, int epi, bf16* kc, bf16* vc, bool p, const bf16* nextW,
+                    unsigned long long next_elems) {
       g.X = X; g.W = W; g.bias = bias; g.res = res; g.Y = Y; g.N = N; g.K = K; g.act = act; g.ln_w = lw; g.ln_b = lb;
       g.epi = epi; g.kcache = kc; g.vtcache = vc; g.pdl = p;
+      g.next_w = (l2pf && ((l2mask >> which) & 1)) ? nextW : nullptr;
+      g.next_bytes = std::min(next_elems * 2ull, l2cap);
       launch_gemv_ring(g, st);
     };
+    const unsigned long long n_qkv = (unsigned long long)e->qkv_cols * H, n_proj = (unsigned long long)H * H,
+                             n_fc = (unsigned long long)d.n_inner * H, n_lm = (unsigned long long)d.vocab * H;
     for (int i = 0; i < d.n_layer; ++i) {
       const DecLayer& L = e->dec[i];
       bf16* kc = e->kcache + e->cache_layer_stride * i;
       bf16* vc = e->vtcache + e->cache_layer_stride * i;
-      gemv(e->d_x, L.attn_w, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, 1, kc, vc, pdl && !first);
+      const bool last = i + 1 == d.n_layer;
+      const bf16* next_first = last ? e->lm_head : e->dec[i + 1].attn_w;       // what follows this layer's mlp.c_proj
+      which = 0;
+      gemv(e->d_x, L.attn_w, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, 1, kc, vc,
+           pdl && !first, L.proj_w, n_proj);
       first = false;
       attention(kc, vc);
-      gemv(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, H, H, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
-      gemv(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b, 0, nullptr, nullptr, pdl);
-      gemv(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
+      which = 1;
+      gemv(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, H, H, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl,
+           L.fc_w, n_fc);
+      which = 2;
+      gemv(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b, 0, nullptr, nullptr,
+           pdl, L.fc2_w, n_fc);
+      which = 3;
+      gemv(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl,
+           next_first, last ? n_lm : n_qkv);
     }
-    gemv(e->d_x, e->lm_head, nullptr, nullptr, e->logits, d.vocab, H, SV_ACT_NONE, e->lnf_w, e->lnf_b, 2, nullptr, nullptr, pdl);
+    which = 4;
+    gemv(e->d_x, e->lm_head, nullptr, nullptr, e->logits, d.vocab, H, SV_ACT_NONE, e->lnf_w, e->lnf_b, 2, nullptr, nullptr,
+         pdl, e->dec[0].attn_w, n_qkv);
     return SV_OK;
   }
   for (int i = 0; i < d.n_layer; ++i) {
@@ -492,6 +517,8 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
   const char* at = getenv("SV_ATTN");             // "ticket" = global-scratch + atomic-ticket merge instead of the cluster/DSMEM merge
   if (at && !strcmp(at, "ticket")) e->use_cluster_attn = false;
+  const char* pf = getenv("SV_L2_PREFETCH");      // "1" = prefetch the next GEMV's weights into L2 (measured: no gain, off)
+  e->use_l2_prefetch = pf && !strcmp(pf, "1");
   const char* rg = getenv("SV_GEMV");             // "regs" = register-landing GEMV kernels instead of the smem weight ring
   if (rg && !strcmp(rg, "regs")) e->use_ring = false;
   if (!gemv_ring_supported(d.hidden, true) || !gemv_ring_supported(d.n_inner, false)) e->use_ring = false;
@@ -851,9 +878,9 @@ int sv_debug_read_timeline(sv_engine* e, long long* out_host, int32_t n) {
 const char* sv_engine_describe(sv_engine* e) {
   if (!e) return "";
   char buf[512];
-  snprintf(buf, sizeof(buf), "decode=%s attn=%s pdl=%d linear_impl=%d mega[%s]",
+  snprintf(buf, sizeof(buf), "decode=%s attn=%s pdl=%d l2pf=%d linear_impl=%d mega[%s]",
            !e->fused_decode ? "legacy-kernels" : (e->use_mega ? "persistent-kernel" : (e->use_ring ? "ring-gemv-graph" : "reg-gemv-graph")),
-           e->use_cluster_attn ? "cluster-dsmem" : "ticket", (int)e->use_pdl, e->linear_impl, decode_mega_status());
+           e->use_cluster_attn ? "cluster-dsmem" : "ticket", (int)e->use_pdl, (int)e->use_l2_prefetch, e->linear_impl, decode_mega_status());
   e->describe = buf;
   return e->describe.c_str();
 }

@@ -141,6 +141,8 @@ struct RingGemvLaunch {
   float* amax_val;
   int* amax_idx;
   bool pdl;
+  const void* next_w;               // next GEMV's weight matrix to prefetch into L2 (nullptr = none)
+  unsigned long long next_bytes;
 };
 cudaError_t gemv_ring_init();
 bool gemv_ring_supported(int K, bool has_ln);
