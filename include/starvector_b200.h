@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SV_ABI_VERSION 1
+#define SV_ABI_VERSION 2
 #if defined(__GNUC__)
 #define SV_API __attribute__((visibility("default")))
 #else
@@ -35,7 +35,7 @@ enum {
   SV_OK = 0,
   SV_ERR_INVALID = -1,     /* bad argument / shape / name */
   SV_ERR_CUDA = -2,        /* CUDA runtime or driver error (message has the cudaError string) */
-  SV_ERR_UNSUPPORTED = -3, /* valid request this build does not implement (e.g. variant 1 = 8B) */
+  SV_ERR_UNSUPPORTED = -3, /* valid request this build does not implement */
   SV_ERR_STATE = -4        /* call order violated (weights missing, no prefill before generate, ...) */
 };
 
@@ -57,7 +57,9 @@ typedef struct sv_engine sv_engine;
 /* Dimensions of one StarVector model (reference: image_encoder.py:50-61,
  * starvector_base.py:87-104, adapters/adapter.py:13-31, bigcode/starcoderbase-1b config). */
 typedef struct sv_model_desc {
-  int32_t variant;      /* 0 = v1: CLIP ViT + Adapter + GPTBigCode (MQA).  1 = v2 (8B): unsupported */
+  int32_t variant;      /* 0 = v1 (1B): CLIP ViT-L/14 + Adapter + GPTBigCode (MQA, learned positions).
+                           1 = v2 (8B): SigLIP tower (no class token, LN eps 1e-6, gelu_tanh, patch bias, post_layernorm)
+                               + StarCoder2 (GQA, RoPE, sliding-window attention, biased linears) — models/starvector_v2.py */
   int32_t image_size;   /* 224 */
   int32_t patch_size;   /* 14  */
   int32_t vit_width;    /* 1024 */
@@ -76,6 +78,10 @@ typedef struct sv_model_desc {
   float ln_eps;         /* 1e-5 */
   int32_t max_batch;    /* images per call on this GPU */
   int32_t max_len;      /* KV-cache capacity in tokens (prefix + generated) */
+  /* v2 only (ignored for variant 0) */
+  float rope_theta;       /* StarCoder2 rope_theta (hub config of bigcode/starcoder2-7b; default 10000 in transformers) */
+  int32_t sliding_window; /* 4096 for starcoder2-7b; 0 = full causal attention */
+  float vit_ln_eps;       /* 1e-6 for SigLIP (1e-5 is used for variant 0) */
 } sv_model_desc;
 
 /* Decoding parameters = the kwargs the reference forwards to HF generate()

@@ -22,8 +22,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from oracle import ref_shim  # noqa: E402
-from oracle.pipeline import OracleStarVector, VIS, LNV, ADP  # noqa: E402
-from starvector_b200.config import dims_tiny  # noqa: E402
+from oracle.pipeline import OracleStarVector, OracleStarVectorV2, VIS, LNV, ADP  # noqa: E402
+from starvector_b200.config import dims_tiny, dims_tiny_v2  # noqa: E402
 from starvector_b200.weights import synthetic_state_dict, synthetic_images  # noqa: E402
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
@@ -74,6 +74,32 @@ def main() -> None:
         path = os.path.join(GOLDEN_DIR, f"tiny_v1_{norm}.pt")
         torch.save(out, path)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+    # v2 (8B family): both towers are third-party transformers classes the reference loads by name; the reference's
+    # own Adapter module is run on the SigLIP output.  40 new tokens cross the tiny config's 24-token sliding window.
+    d = dims_tiny_v2()
+    sd = synthetic_state_dict(d, seed=0, init="randomized")
+    img = synthetic_images(d, 2, seed=1)
+    out = {"dims": d.__dict__.copy(), "seed": 0, "init": "randomized", "image_seed": 1, "prompt_ids": PROMPT_IDS,
+           "stop_ids": STOP_IDS}
+    _, _, AD = ref_shim.load()
+    for tag, dt in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        o = OracleStarVectorV2(d, sd, dtype=dt)
+        n_new = 40
+        vit = o.image_encoder(img.to(dt))
+        ad = AD(d.vit_width, d.hidden, adapter_norm="layer_norm", query_length=d.query_length)
+        ad.load_state_dict({k[len(ADP):]: v for k, v in sd.items() if k.startswith(ADP)})
+        ad = ad.to(dt).eval()
+        with torch.no_grad():
+            out[f"vit_out_{tag}"], out[f"adapter_out_{tag}"] = vit, ad(vit)
+        ids, logits = o.generate_im2svg_ids(img, PROMPT_IDS, STOP_IDS, return_logits=True, use_nucleus_sampling=False,
+                                            num_beams=1, max_length=d.query_length + len(PROMPT_IDS) + n_new)
+        g = torch.Generator().manual_seed(7)
+        forced = torch.randint(1, d.vocab - 5, (2, n_new), generator=g)
+        out[f"greedy_ids_{tag}"], out[f"greedy_logits_{tag}"], out["forced_ids"] = ids, logits, forced
+        out[f"tf_logits_{tag}"] = o.teacher_forced_logits(img, PROMPT_IDS, forced)
+    path = os.path.join(GOLDEN_DIR, "tiny_v2_layer_norm.pt")
+    torch.save(out, path)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":

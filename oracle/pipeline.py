@@ -181,3 +181,98 @@ class OracleStarVector:
         emb = torch.cat([inputs_embeds, self.llm.transformer.wte(forced)], dim=1)
         out = self.llm(inputs_embeds=emb, use_cache=False)
         return out.logits[:, t0 - 1:, :].float()
+
+
+# ======================================================================================================
+# StarVector v2 (8B family): SigLIP vision tower + Adapter + StarCoder2 — reference models/starvector_v2.py,
+# image_encoder.py:32-48,108-109 and llm/starcoder2.py:19-32.  Both towers are the installed transformers
+# classes the reference loads by name; only the glue is restated.
+def build_hf_siglip(dims, sd, dtype):
+    """`AutoModel.from_pretrained("google/siglip-...").vision_model` with random-init weights of our state dict."""
+    from transformers import SiglipVisionConfig, SiglipVisionModel
+
+    cfg = SiglipVisionConfig(hidden_size=dims.vit_width, intermediate_size=dims.vit_mlp, num_hidden_layers=dims.vit_layers,
+                             num_attention_heads=dims.vit_heads, image_size=dims.image_size, patch_size=dims.patch_size,
+                             hidden_act="gelu_pytorch_tanh", layer_norm_eps=dims.vit_ln_eps, attention_dropout=0.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        vm = SiglipVisionModel(cfg).vision_model.to(dtype)
+    vis = _sub(sd, VIS, dtype)
+    missing, unexpected = vm.load_state_dict(vis, strict=False)
+    missing = [m for m in missing if not m.startswith("head.")]      # pooling head: output discarded by the reference
+    if missing or unexpected:
+        raise RuntimeError(f"siglip state dict mismatch: missing={missing[:5]} unexpected={unexpected[:5]}")
+    return vm.eval()
+
+
+def build_hf_starcoder2(dims, sd, dtype, eos_token_id):
+    from transformers import Starcoder2Config, Starcoder2ForCausalLM
+
+    cfg = Starcoder2Config(
+        vocab_size=dims.vocab, hidden_size=dims.hidden, intermediate_size=dims.n_inner, num_hidden_layers=dims.n_layer,
+        num_attention_heads=dims.n_head, num_key_value_heads=dims.n_kv_head, hidden_act="gelu_pytorch_tanh",
+        max_position_embeddings=dims.n_positions, norm_epsilon=dims.ln_eps, use_cache=True,
+        bos_token_id=eos_token_id, eos_token_id=eos_token_id, sliding_window=dims.sliding_window or None, use_bias=True,
+        rope_parameters={"rope_type": "default", "rope_theta": float(dims.rope_theta)},
+        residual_dropout=0.0, embedding_dropout=0.0, attention_dropout=0.0,
+    )
+    llm = _sub(sd, LLM, dtype)
+    tied = "lm_head.weight" not in llm or torch.equal(llm["lm_head.weight"], llm["model.embed_tokens.weight"])
+    cfg.tie_word_embeddings = tied                       # an explicit, different lm_head (tests) stays un-tied
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = Starcoder2ForCausalLM(cfg).to(dtype)
+    llm.setdefault("lm_head.weight", llm["model.embed_tokens.weight"])
+    missing, unexpected = model.load_state_dict(llm, strict=False)
+    if missing or unexpected:
+        raise RuntimeError(f"starcoder2 state dict mismatch: missing={missing[:5]} unexpected={unexpected[:5]}")
+    if tied:
+        model.lm_head.weight = model.model.embed_tokens.weight
+    model.eval()
+    model.generation_config.eos_token_id = eos_token_id
+    model.generation_config.bos_token_id = eos_token_id
+    model.generation_config.pad_token_id = None        # v2 passes no pad id: HF falls back to eos (starvector_v2.py:53-57)
+    return model
+
+
+class OracleStarVectorV2(OracleStarVector):
+    """Reference-equivalent StarVector v2 on CPU (models/starvector_v2.py)."""
+
+    def __init__(self, dims, state_dict, dtype=torch.bfloat16, eos_token_id: Optional[int] = 0):
+        self.dims = dims
+        self.dtype = dtype
+        self.adapter_norm = {0: "layer_norm", 1: "batch_norm"}[dims.adapter_norm]
+        self.adp = _sub(state_dict, ADP, dtype)
+        self.eos_token_id = eos_token_id
+        self.pad_token_id = None
+        self.vision = build_hf_siglip(dims, state_dict, dtype)
+        self.llm = build_hf_starcoder2(dims, state_dict, dtype, 0 if eos_token_id is None else eos_token_id)
+
+    @torch.no_grad()
+    def image_encoder(self, image):
+        return self.vision(image)["last_hidden_state"]                              # image_encoder.py:108-109
+
+    @torch.no_grad()
+    def prepare_generation_inputs(self, image, prompt_ids):
+        image = image.to(self.dtype)
+        embedded_image = self.image_projection(self.image_encoder(image))
+        embedded_att = torch.ones(embedded_image.size()[:-1], dtype=torch.long)
+        prompt = torch.tensor([list(prompt_ids)] * image.size(0), dtype=torch.long)
+        attention_mask = torch.cat([embedded_att, torch.ones_like(prompt)], dim=1)
+        inputs_embeds = self.llm.model.embed_tokens(prompt)                         # starvector_v2.py:45-47
+        return torch.cat([embedded_image, inputs_embeds], dim=1), attention_mask, prompt
+
+    def generation_kwargs(self, base, stop_ids):
+        kw = super().generation_kwargs(base, stop_ids)
+        kw.pop("pad_token_id")                                                     # _get_im2svg_specific_kwargs -> {} (v2:53-57)
+        kw.pop("early_stopping")
+        kw["early_stopping"] = True if kw["num_beams"] > 1 else False
+        return kw
+
+    @torch.no_grad()
+    def teacher_forced_logits(self, image, prompt_ids, forced):
+        inputs_embeds, _, _ = self.prepare_generation_inputs(image, prompt_ids)
+        t0 = inputs_embeds.shape[1]
+        emb = torch.cat([inputs_embeds, self.llm.model.embed_tokens(forced)], dim=1)
+        out = self.llm(inputs_embeds=emb, use_cache=False)
+        return out.logits[:, t0 - 1:, :].float()

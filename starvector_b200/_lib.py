@@ -16,14 +16,15 @@ SV_OK, SV_ERR_INVALID, SV_ERR_CUDA, SV_ERR_UNSUPPORTED, SV_ERR_STATE = 0, -1, -2
 SV_DTYPE_BF16, SV_DTYPE_F32, SV_DTYPE_F16 = 0, 1, 2
 SV_ACT_NONE, SV_ACT_QUICKGELU, SV_ACT_GELU_TANH, SV_ACT_SILU = 0, 1, 2, 3
 SV_LINEAR_AUTO, SV_LINEAR_ROWGROUP, SV_LINEAR_TCGEN05 = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ModelDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "variant", "image_size", "patch_size", "vit_width", "vit_layers", "vit_heads", "vit_mlp", "adapter_norm",
         "hidden", "n_layer", "n_head", "n_kv_head", "head_dim", "n_inner", "n_positions", "vocab")] + [
-        ("ln_eps", C.c_float), ("max_batch", C.c_int32), ("max_len", C.c_int32)]
+        ("ln_eps", C.c_float), ("max_batch", C.c_int32), ("max_len", C.c_int32),
+        ("rope_theta", C.c_float), ("sliding_window", C.c_int32), ("vit_ln_eps", C.c_float)]
 
 
 class GenParams(C.Structure):

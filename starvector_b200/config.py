@@ -41,10 +41,15 @@ class ModelDims:
     # engine capacity
     max_batch: int = 8
     max_len: int = 8192           # KV-cache capacity in tokens (<= n_positions for v1)
+    # v2 (SigLIP + StarCoder2) only
+    rope_theta: float = 0.0       # 0 = learned absolute positions (v1)
+    sliding_window: int = 0
+    vit_ln_eps: float = 1e-5
 
     @property
     def query_length(self) -> int:
-        return (self.image_size // self.patch_size) ** 2 + 1
+        # CLIP prepends a class token (clip_model.py:185); SigLIP does not (starvector_base.py:99-104: 576 @384)
+        return (self.image_size // self.patch_size) ** 2 + (1 if self.variant == 0 else 0)
 
     @property
     def patch_k(self) -> int:
@@ -57,7 +62,7 @@ class ModelDims:
     def decoder_weight_bytes(self) -> int:
         """Bytes of bf16 decoder weights streamed per decode step (SURVEY.md §8d `W`)."""
         h, i, kv = self.hidden, self.n_inner, self.n_kv_head * self.head_dim
-        per_layer = (
+        per_layer = (  # identical parameter count for GPTBigCode (packed c_attn) and StarCoder2 (q/k/v/o + biases)
             2 * h + (h + 2 * kv) * h + (h + 2 * kv)      # ln_1, c_attn
             + h * h + h                                   # attn.c_proj
             + 2 * h + i * h + i + h * i + h               # ln_2, mlp
@@ -71,6 +76,29 @@ class ModelDims:
 def dims_1b(max_batch: int = 8, max_len: int = 8192) -> ModelDims:
     """StarVector-1B: CLIP ViT-L/14@224 (23 blocks) + starcoderbase-1b."""
     return ModelDims(max_batch=max_batch, max_len=max_len)
+
+
+def dims_8b(max_batch: int = 4, max_len: int = 16384, rope_theta: float = 1.0e6) -> ModelDims:
+    """StarVector-8B: SigLIP-L/16@384 (24 blocks, 576 tokens) + starcoder2-7b (36 q / 4 kv heads, RoPE, SWA 4096).
+
+    Dimensions from SURVEY.md §8 (configs/models/starvector-8b/im2svg-stack.yaml, modeling_siglip / modeling_starcoder2);
+    `rope_theta` comes from the hub config of bigcode/starcoder2-7b, which is not available offline: pass the real value.
+    """
+    return ModelDims(
+        variant=1, image_size=384, patch_size=16, vit_width=1024, vit_layers=24, vit_heads=16, vit_mlp=4096,
+        hidden=4608, n_layer=32, n_head=36, n_kv_head=4, head_dim=128, n_inner=18432, n_positions=16384, vocab=49157,
+        ln_eps=1e-5, max_batch=max_batch, max_len=max_len, rope_theta=rope_theta, sliding_window=4096, vit_ln_eps=1e-6,
+    )
+
+
+def dims_tiny_v2(max_batch: int = 4, max_len: int = 192, **over) -> ModelDims:
+    """Few-MB model with the 8B family's structure (SigLIP tower, GQA group 2, RoPE, sliding window 24)."""
+    d = ModelDims(
+        variant=1, image_size=64, patch_size=16, vit_width=128, vit_layers=2, vit_heads=2, vit_mlp=512,
+        hidden=512, n_layer=2, n_head=4, n_kv_head=2, head_dim=128, n_inner=1024, n_positions=192, vocab=500,
+        ln_eps=1e-5, max_batch=max_batch, max_len=max_len, rope_theta=10000.0, sliding_window=24, vit_ln_eps=1e-6,
+    )
+    return dataclasses.replace(d, **over)
 
 
 def dims_tiny(max_batch: int = 4, max_len: int = 256, **over) -> ModelDims:
@@ -157,14 +185,20 @@ class StarVectorConfig:
         return c
 
     def to_dims(self, max_batch: int = 8, max_len: int | None = None) -> ModelDims:
-        """Resolve kernel dimensions.  v1 (GPTBigCode) only in this round; v2 raises."""
+        """Resolve kernel dimensions: v1 = CLIP + GPTBigCode, v2 ('starcoder2' in the name, starvector_arch.py:137-145)
+        = SigLIP + StarCoder2."""
         if "starcoder2" in self.starcoder_model_name:
-            raise NotImplementedError(
-                "StarVector-8B (SigLIP + StarCoder2, reference starvector_v2.py) is not built yet; "
-                "see DESIGN.md 'out of scope this round'."
-            )
+            if "siglip" not in self.image_encoder_type:
+                raise NotImplementedError(f"image_encoder_type={self.image_encoder_type!r}: v2 is built for siglip towers")
+            d = dims_8b(max_batch=max_batch, max_len=max_len or self.max_length)
+            d.image_size = self.image_size if self.image_size != 224 else 384
+            d.adapter_norm = {"layer_norm": 0, "batch_norm": 1}[self.adapter_norm]
+            if self.engine_dims:
+                d = dataclasses.replace(d, **self.engine_dims)
+            d.max_len = min(d.max_len, d.n_positions)
+            return d
         if self.image_encoder_type != "clip":
-            raise NotImplementedError(f"image_encoder_type={self.image_encoder_type!r}: only 'clip' is built")
+            raise NotImplementedError(f"image_encoder_type={self.image_encoder_type!r}: only 'clip' is built for v1")
         d = ModelDims(
             image_size=self.image_size,
             hidden=self.hidden_size,

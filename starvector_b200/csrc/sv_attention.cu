@@ -49,7 +49,8 @@ SV_DEVINL void load_q_frag(uint32_t (&qa)[D / 16][4], const bf16* row_lo, bool o
 template <int D, bool CG = false, bool HOIST_V = false>
 SV_DEVINL void attn_core(const uint32_t (&qa)[D / 16][4], const bf16* __restrict__ kbase, int64_t k_row_stride,
                          const bf16* __restrict__ vtbase, int64_t vt_dim_stride, int key_begin, int key_end,
-                         float scale_log2, float (&acc)[D / 8][4], float (&mrow)[2], float (&lrow)[2], int lane) {
+                         float scale_log2, float (&acc)[D / 8][4], float (&mrow)[2], float (&lrow)[2], int lane,
+                         int key_lo = 0) {   // keys < key_lo are masked (sliding-window attention, StarCoder2)
   const int g = lane >> 2, t = lane & 3;
   for (int kb = key_begin; kb < key_end; kb += 32) {
     float s[4][4];
@@ -76,7 +77,8 @@ SV_DEVINL void attn_core(const uint32_t (&qa)[D / 16][4], const bf16* __restrict
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const bool valid = (kb + 8 * t + 2 * j + e) < key_end;
+        const int kidx = kb + 8 * t + 2 * j + e;
+        const bool valid = kidx < key_end && kidx >= key_lo;
         s[j][e] = valid ? s[j][e] * scale_log2 : -INFINITY;
         s[j][2 + e] = valid ? s[j][2 + e] * scale_log2 : -INFINITY;
         mx0 = fmaxf(mx0, s[j][e]);
@@ -176,7 +178,7 @@ void launch_attention_vit(const bf16* qkv, const bf16* vt, bf16* out, int batch,
 template <int D>
 __global__ void __launch_bounds__(kAttnWarps * 32) attention_heads_kernel(
     const bf16* __restrict__ qkv, int ld, const bf16* __restrict__ kcache, const bf16* __restrict__ vtcache,
-    bf16* __restrict__ out, int batch, int seq, int n_head, int n_kv, int tcap, float scale_log2) {
+    bf16* __restrict__ out, int batch, int seq, int n_head, int n_kv, int tcap, float scale_log2, int window) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int tile = blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
   if (tile >= batch * seq * n_kv) return;
@@ -188,8 +190,9 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_heads_kernel(
   float acc[D / 8][4], mrow[2], lrow[2];
   attn_init<D>(acc, mrow, lrow);
   const int64_t bk = (int64_t)b * n_kv + kvh;
-  attn_core<D>(qa, kcache + bk * tcap * D, D, vtcache + bk * D * tcap, tcap, 0, tok + 1, scale_log2, acc, mrow, lrow,
-               lane);
+  const int key_lo = window > 0 ? max(0, tok + 1 - window) : 0;     // HF sliding window: keys in (q - window, q]
+  attn_core<D>(qa, kcache + bk * tcap * D, D, vtcache + bk * D * tcap, tcap, (key_lo / 32) * 32, tok + 1, scale_log2, acc,
+               mrow, lrow, lane, key_lo);
   const float inv0 = 1.0f / quad_sum(lrow[0]), inv1 = 1.0f / quad_sum(lrow[1]);
   bf16* o = out + (int64_t)bt * n_head * D + (int64_t)kvh * group * D;
 #pragma unroll
@@ -203,12 +206,12 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_heads_kernel(
 }
 
 void launch_attention_heads(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache, bf16* out,
-                            int batch, int seq, int n_head, int n_kv, int d, int tcap, cudaStream_t st) {
+                            int batch, int seq, int n_head, int n_kv, int d, int tcap, int window, cudaStream_t st) {
   const int tiles = batch * seq * n_kv;
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   const int ld = q_cols_total;
   attention_heads_kernel<128><<<(tiles + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(
-      qkv, ld, kcache, vtcache, out, batch, seq, n_head, n_kv, tcap, scale_log2);
+      qkv, ld, kcache, vtcache, out, batch, seq, n_head, n_kv, tcap, scale_log2, window);
   count_launch();
 }
 
@@ -221,15 +224,17 @@ template <int D>
 __global__ void __launch_bounds__(32) attention_decode_split_kernel(
     const bf16* __restrict__ qkv, int ld, const bf16* __restrict__ kcache, const bf16* __restrict__ vtcache,
     float* __restrict__ partial, const GenState* __restrict__ state, int n_head, int n_kv, int tcap, int nsplit,
-    float scale_log2) {
+    float scale_log2, int window) {
   const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int group = n_head / n_kv;
   const int nkeys = state->cur_len + 1;                       // the new token's K/V is already appended
-  const int blocks = (nkeys + 31) / 32;
+  const int key_lo = window > 0 ? max(0, nkeys - window) : 0;
+  const int blk_lo = key_lo / 32;
+  const int blocks = (nkeys + 31) / 32 - blk_lo;
   const int per = (blocks + nsplit - 1) / nsplit;
-  const int kb0 = split * per * 32;
-  const int kb1 = min(nkeys, (split + 1) * per * 32);
+  const int kb0 = (blk_lo + split * per) * 32;
+  const int kb1 = min(nkeys, (blk_lo + (split + 1) * per) * 32);
   if (kb0 >= kb1) return;                                     // inactive split: the merge skips it too
   float* pout = partial + (((int64_t)b * n_kv + kvh) * nsplit + split) * (32 + 16 * D);
   float acc[D / 8][4], mrow[2], lrow[2];
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(32) attention_decode_split_kernel(
     load_q_frag<D>(qa, qrow + (int64_t)g * D, g < group, qrow + (int64_t)(g + 8) * D, g + 8 < group, t);
     const int64_t bk = (int64_t)b * n_kv + kvh;
     attn_core<D>(qa, kcache + bk * tcap * D, D, vtcache + bk * D * tcap, tcap, kb0, kb1, scale_log2, acc, mrow, lrow,
-                 lane);
+                 lane, key_lo);
   }
   const float l0 = quad_sum(lrow[0]), l1 = quad_sum(lrow[1]);
   if (t == 0) {
@@ -258,11 +263,12 @@ template <int D>
 __global__ void __launch_bounds__(D) attention_decode_merge_kernel(const float* __restrict__ partial,
                                                                    bf16* __restrict__ out,
                                                                    const GenState* __restrict__ state, int n_head,
-                                                                   int n_kv, int nsplit) {
+                                                                   int n_kv, int nsplit, int window) {
   const int r = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z, dim = threadIdx.x;
   const int group = n_head / n_kv;
   if (r >= group) return;
-  const int blocks = (state->cur_len + 1 + 31) / 32;
+  const int nkeys = state->cur_len + 1;
+  const int blocks = (nkeys + 31) / 32 - (window > 0 ? max(0, nkeys - window) : 0) / 32;
   const int per = (blocks + nsplit - 1) / nsplit;
   const int nact = (blocks + per - 1) / per;                  // splits that had keys (same rule as above)
   const float* p = partial + ((int64_t)b * n_kv + kvh) * nsplit * (32 + 16 * D);
@@ -281,13 +287,13 @@ __global__ void __launch_bounds__(D) attention_decode_merge_kernel(const float* 
 
 void launch_attention_decode(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache, bf16* out,
                              float* partial, const GenState* state, int batch, int n_head, int n_kv, int d, int tcap,
-                             int nsplit, cudaStream_t st) {
+                             int nsplit, int window, cudaStream_t st) {
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   attention_decode_split_kernel<128><<<dim3(nsplit, n_kv, batch), 32, 0, st>>>(qkv, q_cols_total, kcache, vtcache,
                                                                               partial, state, n_head, n_kv, tcap,
-                                                                              nsplit, scale_log2);
+                                                                              nsplit, scale_log2, window);
   attention_decode_merge_kernel<128><<<dim3(n_head / n_kv, n_kv, batch), 128, 0, st>>>(partial, out, state, n_head,
-                                                                                      n_kv, nsplit);
+                                                                                      n_kv, nsplit, window);
   count_launch(2);
 }
 

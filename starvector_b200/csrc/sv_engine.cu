@@ -52,6 +52,10 @@ struct sv_engine {
   int linear_impl = SV_LINEAR_AUTO;
 
   int Q = 0, NP = 0, Kp = 0, Lpad = 0, qkv_cols = 0, tcap = 0;
+  bool v2 = false;                 // SigLIP + StarCoder2 (StarVector-8B family)
+  float vit_eps = 1e-5f;
+  int vit_act = SV_ACT_QUICKGELU, window = 0;
+  bf16 *conv_b = nullptr, *rope_cos = nullptr, *rope_sin = nullptr;
   std::map<std::string, Weight> w;
   std::vector<void*> allocs;
 
@@ -127,16 +131,22 @@ cudaError_t dev_alloc(sv_engine* e, T** p, int64_t n) {
   return r;
 }
 
+// `external` != nullptr registers the name as a view into storage that another entry owns (v2 packs the reference's
+// separate q_proj / k_proj / v_proj tensors into one [q|k|v] matrix so both families share the same kernels).
 bf16* add_weight(sv_engine* e, const std::string& name, std::vector<int64_t> shape, int64_t alloc_numel = -1,
-                 bool optional = false) {
+                 bool optional = false, bf16* external = nullptr) {
   Weight wt;
   wt.shape = shape;
   wt.numel = 1;
   for (auto s : shape) wt.numel *= s;
   wt.optional = optional;
-  int64_t n = alloc_numel > 0 ? alloc_numel : wt.numel;
-  if (dev_alloc(e, &wt.p, n) != cudaSuccess) return nullptr;
-  cudaMemset(wt.p, 0, (size_t)n * sizeof(bf16));
+  if (external) {
+    wt.p = external;
+  } else {
+    int64_t n = alloc_numel > 0 ? alloc_numel : wt.numel;
+    if (dev_alloc(e, &wt.p, n) != cudaSuccess) return nullptr;
+    cudaMemset(wt.p, 0, (size_t)n * sizeof(bf16));
+  }
   bf16* p = wt.p;
   e->w[name] = std::move(wt);
   return p;
@@ -148,7 +158,10 @@ const char* ADP = "model.image_projection.";
 const char* DEC = "model.svg_transformer.transformer.transformer.";
 const char* LMH = "model.svg_transformer.transformer.lm_head.weight";
 
+bool build_weights_v2(sv_engine* e);
+
 bool build_weights(sv_engine* e) {
+  if (e->v2) return build_weights_v2(e);
   const sv_model_desc& d = e->d;
   const int64_t W = d.vit_width, Q = e->Q, H = d.hidden, kv = (int64_t)d.n_kv_head * d.head_dim, I = d.n_inner;
   bool ok = true;
@@ -206,6 +219,80 @@ bool build_weights(sv_engine* e) {
   return ok;
 }
 
+// StarVector v2 (8B family) state dict: SiglipVisionTransformer keys under model.image_encoder.visual_encoder.
+// (image_encoder.py:32-48,108-109), the same Adapter, Starcoder2ForCausalLM keys under
+// model.svg_transformer.transformer. (llm/starcoder2.py:19-32).  q/k/v projections are packed [q|k|v] at load.
+bool build_weights_v2(sv_engine* e) {
+  const sv_model_desc& d = e->d;
+  const int64_t W = d.vit_width, Q = e->Q, H = d.hidden, D = d.head_dim, kv = (int64_t)d.n_kv_head * D, I = d.n_inner;
+  const int64_t HQ = (int64_t)d.n_head * D;
+  bool ok = true;
+  auto A = [&](const std::string& n, std::vector<int64_t> s, bf16* ext = nullptr, bool opt = false) {
+    bf16* p = add_weight(e, n, std::move(s), -1, opt, ext);
+    ok = ok && p != nullptr;
+    return p;
+  };
+  auto raw = [&](int64_t n) { bf16* p = nullptr; ok = ok && dev_alloc(e, &p, n) == cudaSuccess; if (p) cudaMemset(p, 0, (size_t)n * 2); return p; };
+  std::string v = VIS;
+  e->conv_raw = A(v + "embeddings.patch_embedding.weight", {W, 3, d.patch_size, d.patch_size});
+  ok = ok && dev_alloc(e, &e->conv_w, W * e->Kp) == cudaSuccess;
+  e->conv_b = A(v + "embeddings.patch_embedding.bias", {W});
+  e->pos = A(v + "embeddings.position_embedding.weight", {Q, W});
+  e->vit.resize(d.vit_layers);
+  for (int i = 0; i < d.vit_layers; ++i) {
+    std::string p = v + "encoder.layers." + std::to_string(i) + ".";
+    VitLayer& L = e->vit[i];
+    L.ln1_w = A(p + "layer_norm1.weight", {W}); L.ln1_b = A(p + "layer_norm1.bias", {W});
+    L.qkv_w = raw(3 * W * W); L.qkv_b = raw(3 * W);
+    if (!ok) return false;
+    const char* nm[3] = {"q_proj", "k_proj", "v_proj"};
+    for (int j = 0; j < 3; ++j) {
+      A(p + "self_attn." + nm[j] + ".weight", {W, W}, L.qkv_w + j * W * W);
+      A(p + "self_attn." + nm[j] + ".bias", {W}, L.qkv_b + j * W);
+    }
+    L.out_w = A(p + "self_attn.out_proj.weight", {W, W}); L.out_b = A(p + "self_attn.out_proj.bias", {W});
+    L.ln2_w = A(p + "layer_norm2.weight", {W}); L.ln2_b = A(p + "layer_norm2.bias", {W});
+    L.fc_w = A(p + "mlp.fc1.weight", {(int64_t)d.vit_mlp, W}); L.fc_b = A(p + "mlp.fc1.bias", {(int64_t)d.vit_mlp});
+    L.proj_w = A(p + "mlp.fc2.weight", {W, (int64_t)d.vit_mlp}); L.proj_b = A(p + "mlp.fc2.bias", {W});
+  }
+  e->lnv_w = A(v + "post_layernorm.weight", {W});
+  e->lnv_b = A(v + "post_layernorm.bias", {W});
+  std::string a = ADP;
+  e->afc_w = A(a + "c_fc.weight", {2 * W, W}); e->afc_b = A(a + "c_fc.bias", {2 * W});
+  e->aproj_w = A(a + "c_proj.weight", {H, 2 * W}); e->aproj_b = A(a + "c_proj.bias", {H});
+  if (d.adapter_norm == 0) {
+    e->anorm_w = A(a + "norm.weight", {Q, H}); e->anorm_b = A(a + "norm.bias", {Q, H});
+  } else {
+    e->anorm_w = A(a + "norm.weight", {Q}); e->anorm_b = A(a + "norm.bias", {Q});
+    e->anorm_rm = A(a + "norm.running_mean", {Q}); e->anorm_rv = A(a + "norm.running_var", {Q});
+  }
+  std::string t = "model.svg_transformer.transformer.model.";
+  e->wte = A(t + "embed_tokens.weight", {(int64_t)d.vocab, H});
+  e->wpe = nullptr;
+  e->dec.resize(d.n_layer);
+  for (int i = 0; i < d.n_layer; ++i) {
+    std::string p = t + "layers." + std::to_string(i) + ".";
+    DecLayer& L = e->dec[i];
+    L.ln1_w = A(p + "input_layernorm.weight", {H}); L.ln1_b = A(p + "input_layernorm.bias", {H});
+    L.attn_w = raw((HQ + 2 * kv) * H); L.attn_b = raw(HQ + 2 * kv);
+    if (!ok) return false;
+    A(p + "self_attn.q_proj.weight", {HQ, H}, L.attn_w); A(p + "self_attn.q_proj.bias", {HQ}, L.attn_b);
+    A(p + "self_attn.k_proj.weight", {kv, H}, L.attn_w + HQ * H); A(p + "self_attn.k_proj.bias", {kv}, L.attn_b + HQ);
+    A(p + "self_attn.v_proj.weight", {kv, H}, L.attn_w + (HQ + kv) * H); A(p + "self_attn.v_proj.bias", {kv}, L.attn_b + HQ + kv);
+    L.proj_w = A(p + "self_attn.o_proj.weight", {H, HQ}); L.proj_b = A(p + "self_attn.o_proj.bias", {H});
+    L.ln2_w = A(p + "post_attention_layernorm.weight", {H}); L.ln2_b = A(p + "post_attention_layernorm.bias", {H});
+    L.fc_w = A(p + "mlp.c_fc.weight", {I, H}); L.fc_b = A(p + "mlp.c_fc.bias", {I});
+    L.fc2_w = A(p + "mlp.c_proj.weight", {H, I}); L.fc2_b = A(p + "mlp.c_proj.bias", {H});
+  }
+  e->lnf_w = A(t + "norm.weight", {H});
+  e->lnf_b = A(t + "norm.bias", {H});
+  e->lm_head = e->wte;
+  // RoPE tables [n_positions][D/2]: computed on device at create; a host may overwrite them with its own values
+  e->rope_cos = A("engine.rope_cos", {(int64_t)d.n_positions, D / 2}, nullptr, true);
+  e->rope_sin = A("engine.rope_sin", {(int64_t)d.n_positions, D / 2}, nullptr, true);
+  return ok;
+}
+
 bool build_buffers(sv_engine* e) {
   const sv_model_desc& d = e->d;
   const int64_t B = d.max_batch, W = d.vit_width, H = d.hidden, I = d.n_inner, D = d.head_dim;
@@ -260,22 +347,27 @@ int do_linear(sv_engine* e, int impl, const bf16* x, const bf16* w, const bf16* 
 int run_encode(sv_engine* e, const bf16* pixels, int B, cudaStream_t st) {
   const sv_model_desc& d = e->d;
   const int W = d.vit_width, Q = e->Q, NP = e->NP, M = B * Q, H = d.hidden;
+  const float veps = e->vit_eps;
   launch_im2col(pixels, e->v_patches, B, d.image_size, d.patch_size, e->Kp, st);
-  LIN(e->v_patches, e->conv_w, nullptr, nullptr, e->v_pe, B * NP, W, e->Kp, SV_ACT_NONE, st);     // conv1 (no bias)
-  launch_vit_assemble(e->v_pe, e->cls, e->pos, e->v_ln, B, NP, W, st);                             // cat + pos
-  launch_layernorm(e->v_ln, e->lnpre_w, e->lnpre_b, e->v_x, M, W, 1e-5f, W, st);                   // ln_pre
+  LIN(e->v_patches, e->conv_w, e->conv_b, nullptr, e->v_pe, B * NP, W, e->Kp, SV_ACT_NONE, st);   // patch conv (bias: SigLIP only)
+  if (e->v2) {
+    launch_vit_assemble(e->v_pe, nullptr, e->pos, e->v_x, B, NP, W, st);                           // + position_embedding
+  } else {
+    launch_vit_assemble(e->v_pe, e->cls, e->pos, e->v_ln, B, NP, W, st);                           // cat cls + pos
+    launch_layernorm(e->v_ln, e->lnpre_w, e->lnpre_b, e->v_x, M, W, veps, W, st);                  // ln_pre
+  }
   for (int i = 0; i < d.vit_layers; ++i) {
     const VitLayer& L = e->vit[i];
-    launch_layernorm(e->v_x, L.ln1_w, L.ln1_b, e->v_ln, M, W, 1e-5f, W, st);
+    launch_layernorm(e->v_x, L.ln1_w, L.ln1_b, e->v_ln, M, W, veps, W, st);
     LIN(e->v_ln, L.qkv_w, L.qkv_b, nullptr, e->v_qkv, M, 3 * W, W, SV_ACT_NONE, st);
     launch_vit_transpose_v(e->v_qkv, e->v_vt, B, Q, d.vit_heads, e->Lpad, st);
     launch_attention_vit(e->v_qkv, e->v_vt, e->v_attn, B, Q, d.vit_heads, e->Lpad, st);
     LIN(e->v_attn, L.out_w, L.out_b, e->v_x, e->v_x, M, W, W, SV_ACT_NONE, st);                    // x += attn
-    launch_layernorm(e->v_x, L.ln2_w, L.ln2_b, e->v_ln, M, W, 1e-5f, W, st);
-    LIN(e->v_ln, L.fc_w, L.fc_b, nullptr, e->v_h, M, d.vit_mlp, W, SV_ACT_QUICKGELU, st);
+    launch_layernorm(e->v_x, L.ln2_w, L.ln2_b, e->v_ln, M, W, veps, W, st);
+    LIN(e->v_ln, L.fc_w, L.fc_b, nullptr, e->v_h, M, d.vit_mlp, W, e->vit_act, st);
     LIN(e->v_h, L.proj_w, L.proj_b, e->v_x, e->v_x, M, W, d.vit_mlp, SV_ACT_NONE, st);             // x += mlp
   }
-  launch_layernorm(e->v_x, e->lnv_w, e->lnv_b, e->v_out, M, W, 1e-5f, W, st);                      // ln_vision
+  launch_layernorm(e->v_x, e->lnv_w, e->lnv_b, e->v_out, M, W, veps, W, st);                       // ln_vision | post_layernorm
   LIN(e->v_out, e->afc_w, e->afc_b, nullptr, e->a_h, M, 2 * W, W, SV_ACT_SILU, st);
   LIN(e->a_h, e->aproj_w, e->aproj_b, nullptr, e->a_z, M, H, 2 * W, SV_ACT_NONE, st);
   if (d.adapter_norm == 0)
@@ -298,8 +390,10 @@ int run_prefill(sv_engine* e, const bf16* prefix, int q, const int32_t* prompt_i
     bf16* vc = e->vtcache + e->cache_layer_stride * i;
     launch_layernorm(e->p_x, L.ln1_w, L.ln1_b, e->p_ln, M, H, d.ln_eps, H, st);
     LIN(e->p_ln, L.attn_w, L.attn_b, nullptr, e->p_qkv, M, e->qkv_cols, H, SV_ACT_NONE, st);
+    if (e->v2)   // RoPE on q and k (positions 0..T0-1), modeling_starcoder2.py:167-168
+      launch_rope(e->p_qkv, M, T0, e->qkv_cols, d.n_head + d.n_kv_head, D, e->rope_cos, e->rope_sin, nullptr, d.n_positions, st);
     launch_kv_scatter(e->p_qkv, kc, vc, B, T0, d.n_head * D, d.n_kv_head, D, e->tcap, 0, st);
-    launch_attention_heads(e->p_qkv, e->qkv_cols, kc, vc, e->p_attn, B, T0, d.n_head, d.n_kv_head, D, e->tcap, st);
+    launch_attention_heads(e->p_qkv, e->qkv_cols, kc, vc, e->p_attn, B, T0, d.n_head, d.n_kv_head, D, e->tcap, e->window, st);
     LIN(e->p_attn, L.proj_w, L.proj_b, e->p_x, e->p_x, M, H, H, SV_ACT_NONE, st);
     launch_layernorm(e->p_x, L.ln2_w, L.ln2_b, e->p_ln, M, H, d.ln_eps, H, st);
     LIN(e->p_ln, L.fc_w, L.fc_b, nullptr, e->p_h, M, d.n_inner, H, SV_ACT_GELU_TANH, st);
@@ -323,9 +417,11 @@ int run_decode_layers(sv_engine* e, const int32_t* ids, int B, int nsplit, cudaS
     bf16* vc = e->vtcache + e->cache_layer_stride * i;
     launch_layernorm(e->d_x, L.ln1_w, L.ln1_b, e->d_ln, B, H, d.ln_eps, H, st);
     launch_linear_rowgroup(e->d_ln, L.attn_w, L.attn_b, nullptr, e->d_qkv, B, e->qkv_cols, H, SV_ACT_NONE, st);
+    if (e->v2)
+      launch_rope(e->d_qkv, B, 1, e->qkv_cols, d.n_head + d.n_kv_head, D, e->rope_cos, e->rope_sin, e->state, d.n_positions, st);
     launch_kv_append(e->d_qkv, kc, vc, e->state, B, d.n_head * D, d.n_kv_head, D, e->tcap, st);
     launch_attention_decode(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->attn_partial, e->state, B, d.n_head,
-                            d.n_kv_head, D, e->tcap, nsplit, st);
+                            d.n_kv_head, D, e->tcap, nsplit, e->window, st);
     launch_linear_rowgroup(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, B, H, H, SV_ACT_NONE, st);
     launch_layernorm(e->d_x, L.ln2_w, L.ln2_b, e->d_ln, B, H, d.ln_eps, H, st);
     launch_linear_rowgroup(e->d_ln, L.fc_w, L.fc_b, nullptr, e->d_h, B, d.n_inner, H, SV_ACT_GELU_TANH, st);
@@ -470,10 +566,12 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   if (!desc || !out) return fail(nullptr, SV_ERR_INVALID, "null argument");
   *out = nullptr;
   const sv_model_desc& d = *desc;
-  if (d.variant != 0)
-    return fail(nullptr, SV_ERR_UNSUPPORTED, "variant %d (SigLIP + StarCoder2, StarVector-8B) is not built in this round", d.variant);
+  if (d.variant != 0 && d.variant != 1) return fail(nullptr, SV_ERR_UNSUPPORTED, "unknown model variant %d", d.variant);
+  if (d.variant == 1 && !(d.rope_theta > 1.0f)) return fail(nullptr, SV_ERR_INVALID, "variant 1 (StarCoder2) needs rope_theta > 1");
+  if (d.variant == 1 && d.sliding_window < 0) return fail(nullptr, SV_ERR_INVALID, "sliding_window must be >= 0");
   if (d.vit_width != d.vit_heads * 64) return fail(nullptr, SV_ERR_INVALID, "ViT head dim must be 64");
   if (d.head_dim != 128 || d.hidden != d.n_head * d.head_dim) return fail(nullptr, SV_ERR_INVALID, "decoder head dim must be 128 and hidden == n_head*128");
+  if (d.hidden % 64 || d.n_inner % 64) return fail(nullptr, SV_ERR_INVALID, "decoder widths must be multiples of 64");
   if (d.n_kv_head < 1 || d.n_head % d.n_kv_head || d.n_head / d.n_kv_head > 16) return fail(nullptr, SV_ERR_INVALID, "need 1 <= n_head/n_kv_head <= 16");
   if (d.image_size % d.patch_size) return fail(nullptr, SV_ERR_INVALID, "image_size %% patch_size != 0");
   if (d.vit_width % 64 || d.vit_mlp % 64 || d.hidden % 64 || d.n_inner % 64) return fail(nullptr, SV_ERR_INVALID, "widths must be multiples of 64");
@@ -496,7 +594,13 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   e->device = device;
   const int g = d.image_size / d.patch_size;
   e->NP = g * g;
-  e->Q = e->NP + 1;
+  e->v2 = d.variant == 1;
+  e->Q = e->NP + (e->v2 ? 0 : 1);                       // SigLIP has no class token
+  if (e->v2) {
+    e->vit_eps = d.vit_ln_eps > 0.f ? d.vit_ln_eps : 1e-6f;
+    e->vit_act = SV_ACT_GELU_TANH;
+    e->window = d.sliding_window;
+  }
   e->Kp = (3 * d.patch_size * d.patch_size + 63) / 64 * 64;
   e->Lpad = (e->Q + 31) / 32 * 32;
   e->qkv_cols = d.hidden + 2 * d.n_kv_head * d.head_dim;
@@ -512,6 +616,7 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   const char* pdl = getenv("SV_PDL");             // "0" = plain stream order between decode kernels
   if (pdl && !strcmp(pdl, "0")) e->use_pdl = false;
   if (!gemv8_supported(d.hidden, true) || !gemv8_supported(d.n_inner, false)) e->fused_decode = false;
+  if (e->v2) e->fused_decode = false;             // v2 decodes on the per-op kernels (+RoPE, sliding window) this round
   const char* mg = getenv("SV_MEGA");             // "1" = persistent multi-token kernel instead of the per-phase CUDA graph
   e->use_mega = mg && !strcmp(mg, "1");           // (opt-in until it beats the graph path: DESIGN.md "decode modes")
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
@@ -526,6 +631,13 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
     std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     sv_engine_destroy(e);
     return fail(nullptr, SV_ERR_CUDA, "%s", msg.c_str());
+  }
+  if (e->v2) {
+    launch_rope_table(e->rope_cos, e->rope_sin, d.n_positions, d.head_dim, d.rope_theta, nullptr);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      sv_engine_destroy(e);
+      return fail(nullptr, SV_ERR_CUDA, "RoPE table setup failed");
+    }
   }
   {
     std::vector<MegaLayer> ml(d.n_layer);
@@ -577,8 +689,10 @@ int sv_engine_load_weight(sv_engine* e, const char* hf_name, const void* data, c
   std::string name = hf_name;
   auto ends_with = [&](const char* s) { size_t n = strlen(s); return name.size() >= n && !name.compare(name.size() - n, n, s); };
   if (ends_with("num_batches_tracked") || ends_with(".attn.bias") || ends_with("transformer.bias") ||
-      ends_with(".attn.masked_bias"))
+      ends_with(".attn.masked_bias") || ends_with("rotary_emb.inv_freq") || ends_with("embeddings.position_ids"))
     return SV_OK;   // buffers that carry no parameters
+  if (name.find("visual_encoder.head.") != std::string::npos)
+    return SV_OK;   // SigLIP pooling head: computed and discarded by the reference (image_encoder.py:109)
   int64_t numel = 1;
   for (int i = 0; i < ndim; ++i) numel *= shape[i];
   if (name == LMH && e->w.find(name) == e->w.end()) {   // explicit (un-tied) lm_head
@@ -942,7 +1056,7 @@ int sv_op_attention_mqa(const void* qkv, void* out, int32_t batch, int32_t seq, 
   bf16* vc = kc + n;
   cudaMemsetAsync(kc, 0, 2 * n * 2, st);
   launch_kv_scatter((const bf16*)qkv, kc, vc, batch, seq, heads * D, 1, D, tcap, 0, st);
-  launch_attention_heads((const bf16*)qkv, heads * D + 2 * D, kc, vc, (bf16*)out, batch, seq, heads, 1, D, tcap, st);
+  launch_attention_heads((const bf16*)qkv, heads * D + 2 * D, kc, vc, (bf16*)out, batch, seq, heads, 1, D, tcap, 0, st);
   r = cudaStreamSynchronize(st);
   cudaFree(kc);
   return r == cudaSuccess ? SV_OK : op_fail("attention_mqa", r);

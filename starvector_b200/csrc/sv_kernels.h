@@ -34,7 +34,7 @@ void launch_convert_to_bf16(const void* src, int dtype, bf16* dst, int64_t n, cu
 void launch_pad_rows(const bf16* src, bf16* dst, int rows, int src_cols, int dst_cols, cudaStream_t st);
 void launch_im2col(const bf16* pixels, bf16* patches, int batch, int image, int patch, int kpad, cudaStream_t st);
 void launch_vit_assemble(const bf16* pe, const bf16* cls, const bf16* pos, bf16* x, int batch, int np, int width,
-                         cudaStream_t st);
+                         cudaStream_t st);   // cls == nullptr: no class token (SigLIP): x = pe + pos
 void launch_vit_transpose_v(const bf16* qkv, bf16* vt, int batch, int seq, int heads, int seq_pad, cudaStream_t st);
 void launch_slab_layernorm(const bf16* z, const bf16* w, const bf16* b, bf16* y, float* partial, int batch,
                            int64_t slab, float eps, cudaStream_t st);
@@ -73,10 +73,15 @@ void launch_attention_vit(const bf16* qkv, const bf16* vt, bf16* out, int batch,
                           cudaStream_t st);
 // causal attention of `seq` new tokens per row against the cache (prefill: cache already holds them)
 void launch_attention_heads(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache, bf16* out,
-                            int batch, int seq, int n_head, int n_kv, int d, int tcap, cudaStream_t st);
+                            int batch, int seq, int n_head, int n_kv, int d, int tcap, int window, cudaStream_t st);
 void launch_attention_decode(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache, bf16* out,
                              float* partial, const GenState* state, int batch, int n_head, int n_kv, int d, int tcap,
-                             int nsplit, cudaStream_t st);
+                             int nsplit, int window, cudaStream_t st);
+// RoPE in place on the q and k parts of packed qkv rows [rows][qkv_cols] (StarCoder2, rotate_half convention);
+// cos/sin tables are bf16 [max_pos][D/2]; position of row r = pos0 + (r % seq) or state->cur_len when state != nullptr.
+void launch_rope(bf16* qkv, int rows, int seq, int qkv_cols, int n_rot_heads, int d, const bf16* cos_t, const bf16* sin_t,
+                 const GenState* state, int max_pos, cudaStream_t st);
+void launch_rope_table(bf16* cos_t, bf16* sin_t, int max_pos, int d, float theta, cudaStream_t st);
 
 // fused decode attention (PDL-ready): ncta from attention_decode_fused_ncta(max total length)
 int attention_decode_fused_ncta(int total_len);

@@ -120,16 +120,17 @@ void launch_im2col(const bf16* pixels, bf16* patches, int batch, int image, int 
 // cat([class_embedding, patches]) + positional_embedding (clip_model.py:185-186); bf16 add.
 __global__ void vit_assemble_kernel(const bf16* __restrict__ pe, const bf16* __restrict__ cls,
                                     const bf16* __restrict__ pos, bf16* __restrict__ x, int np, int width) {
-  const int q = np + 1;
+  const int off = cls ? 1 : 0;                     // SigLIP has no class token (modeling_siglip.py:178-187)
+  const int q = np + off;
   const int b = blockIdx.x / q, t = blockIdx.x % q;
-  const bf16* src = t == 0 ? cls : pe + ((int64_t)b * np + (t - 1)) * width;
+  const bf16* src = (cls && t == 0) ? cls : pe + ((int64_t)b * np + (t - off)) * width;
   for (int c = threadIdx.x; c < width; c += blockDim.x)
     x[(int64_t)blockIdx.x * width + c] =
         __float2bfloat16_rn(__bfloat162float(src[c]) + __bfloat162float(pos[(int64_t)t * width + c]));
 }
 void launch_vit_assemble(const bf16* pe, const bf16* cls, const bf16* pos, bf16* x, int batch, int np, int width,
                          cudaStream_t st) {
-  vit_assemble_kernel<<<batch * (np + 1), 128, 0, st>>>(pe, cls, pos, x, np, width);
+  vit_assemble_kernel<<<batch * (np + (cls ? 1 : 0)), 128, 0, st>>>(pe, cls, pos, x, np, width);
   count_launch();
 }
 
@@ -247,13 +248,15 @@ __global__ void embed_prefix_kernel(const bf16* __restrict__ visual, const int32
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
     src = wte + (int64_t)id * h;
   }
-  const bf16* pos = wpe + (int64_t)t * h;
+  const bf16* pos = wpe ? wpe + (int64_t)t * h : nullptr;   // RoPE models (StarCoder2) have no learned positions
   for (int c = threadIdx.x * 8; c < h; c += blockDim.x * 8) {
     float a[8], d[8];
     unpack8(ldg_cached(src + c), a);
-    unpack8(ldg_cached(pos + c), d);
+    if (pos) {
+      unpack8(ldg_cached(pos + c), d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] += d[j];
+      for (int j = 0; j < 8; ++j) a[j] += d[j];
+    }
     *reinterpret_cast<uint4*>(x + (int64_t)blockIdx.x * h + c) = pack8(a);
   }
 }
@@ -272,13 +275,15 @@ __global__ void embed_tokens_kernel(const int32_t* __restrict__ ids, const bf16*
   int pos = state->cur_len;
   pos = pos >= n_positions ? n_positions - 1 : pos;
   const bf16* src = wte + (int64_t)id * h;
-  const bf16* pe = wpe + (int64_t)pos * h;
+  const bf16* pe = wpe ? wpe + (int64_t)pos * h : nullptr;
   for (int c = threadIdx.x * 8; c < h; c += blockDim.x * 8) {
     float a[8], d[8];
     unpack8(ldg_cached(src + c), a);
-    unpack8(ldg_cached(pe + c), d);
+    if (pe) {
+      unpack8(ldg_cached(pe + c), d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] += d[j];
+      for (int j = 0; j < 8; ++j) a[j] += d[j];
+    }
     *reinterpret_cast<uint4*>(x + (int64_t)b * h + c) = pack8(a);
   }
 }
@@ -531,6 +536,46 @@ void launch_advance_len(GenState* state, cudaStream_t st) {
   advance_len_kernel<<<1, 32, 0, st>>>(state);
   count_launch();
 }
+
+// ------------------------------------------------------------------------------------------
+// Rotary position embedding of StarCoder2 (transformers modeling_starcoder2.py:72-107,265-329): cos/sin are computed
+// in fp32, CAST TO bf16, and  q*cos + rotate_half(q)*sin  runs as three bf16 tensor ops (two products, one sum).
+__global__ void rope_table_kernel(bf16* __restrict__ cos_t, bf16* __restrict__ sin_t, int max_pos, int half, float theta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= max_pos * half) return;
+  const int pos = i / half, j = i % half;
+  const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)(2 * half));
+  const float ang = (float)pos * inv_freq;
+  cos_t[i] = __float2bfloat16_rn(cosf(ang));
+  sin_t[i] = __float2bfloat16_rn(sinf(ang));
+}
+void launch_rope_table(bf16* cos_t, bf16* sin_t, int max_pos, int d, float theta, cudaStream_t st) {
+  const int n = max_pos * (d / 2);
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(cos_t, sin_t, max_pos, d / 2, theta);
+  count_launch();
+}
+__global__ void rope_kernel(bf16* __restrict__ qkv, int seq, int qkv_cols, int n_rot_heads, int d,
+                            const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+                            const GenState* __restrict__ state, int max_pos) {
+  const int row = blockIdx.x, half = d >> 1;
+  int pos = state ? state->cur_len : (row % seq);
+  pos = pos >= max_pos ? max_pos - 1 : pos;
+  bf16* base = qkv + (int64_t)row * qkv_cols;
+  for (int i = threadIdx.x; i < n_rot_heads * half; i += blockDim.x) {
+    const int h = i / half, j = i % half;
+    bf16* v = base + h * d;
+    const float c = __bfloat162float(cos_t[(int64_t)pos * half + j]), s = __bfloat162float(sin_t[(int64_t)pos * half + j]);
+    const float x1 = __bfloat162float(v[j]), x2 = __bfloat162float(v[j + half]);
+    v[j] = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * s));
+    v[j + half] = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
+  }
+}
+void launch_rope(bf16* qkv, int rows, int seq, int qkv_cols, int n_rot_heads, int d, const bf16* cos_t, const bf16* sin_t,
+                 const GenState* state, int max_pos, cudaStream_t st) {
+  rope_kernel<<<rows, 256, 0, st>>>(qkv, seq, qkv_cols, n_rot_heads, d, cos_t, sin_t, state, max_pos);
+  count_launch();
+}
+
 __global__ void fill_i32_kernel(int32_t* p, int32_t v, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

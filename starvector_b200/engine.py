@@ -71,6 +71,7 @@ class Engine:
             hidden=dims.hidden, n_layer=dims.n_layer, n_head=dims.n_head, n_kv_head=dims.n_kv_head,
             head_dim=dims.head_dim, n_inner=dims.n_inner, n_positions=dims.n_positions, vocab=dims.vocab,
             ln_eps=dims.ln_eps, max_batch=dims.max_batch, max_len=dims.max_len,
+            rope_theta=dims.rope_theta, sliding_window=dims.sliding_window, vit_ln_eps=dims.vit_ln_eps,
         )
         h = C.c_void_p()
         torch.cuda.init()
@@ -100,7 +101,8 @@ class Engine:
     # -- weights -------------------------------------------------------------------------
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True) -> None:
         """Copy a reference-named state dict (CPU or CUDA tensors; bf16/fp16/fp32) into the engine."""
-        wte_key = "model.svg_transformer.transformer.transformer.wte.weight"
+        wte_key = ("model.svg_transformer.transformer.model.embed_tokens.weight" if self.dims.variant == 1
+                   else "model.svg_transformer.transformer.transformer.wte.weight")
         lm_key = "model.svg_transformer.transformer.lm_head.weight"
         with self._lock:
             for name, t in sd.items():
@@ -118,10 +120,24 @@ class Engine:
                 if code == _lib.SV_ERR_INVALID and not strict:
                     continue
                 self._ck(code)
+            if self.dims.variant == 1:
+                self._load_rope_tables()
             missing = self._lib.sv_engine_missing_weights(self._h)
             if missing and strict:
                 names = self._lib.sv_last_error(self._h).decode()
                 raise KeyError(f"{missing} weights missing from state dict, e.g. {names.splitlines()[:4]}")
+
+    def _load_rope_tables(self) -> None:
+        """cos/sin tables computed exactly as Starcoder2RotaryEmbedding does (fp32 outer product, cast to bf16), so the
+        engine's RoPE inputs are bit-identical to the reference's; the engine's own on-device table is the fallback."""
+        d = self.dims
+        inv_freq = 1.0 / (d.rope_theta ** (torch.arange(0, d.head_dim, 2, dtype=torch.int64).float() / d.head_dim))
+        freqs = torch.outer(torch.arange(d.n_positions, dtype=torch.float32), inv_freq)
+        for name, t in (("engine.rope_cos", freqs.cos()), ("engine.rope_sin", freqs.sin())):
+            t = t.to(torch.bfloat16).contiguous()
+            shape = (C.c_int64 * 2)(*t.shape)
+            self._ck(self._lib.sv_engine_load_weight(self._h, name.encode(), C.c_void_p(t.data_ptr()), shape, 2,
+                                                     _lib.SV_DTYPE_BF16))
 
     # -- stages --------------------------------------------------------------------------
     def _dev(self, t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:

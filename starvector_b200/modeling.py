@@ -21,7 +21,7 @@ import torch
 from .config import ModelDims, StarVectorConfig
 from .engine import Engine, GenerationParams
 from .tokenizer import load_tokenizer
-from .weights import DEC, synthetic_state_dict
+from .weights import DEC, DEC2, synthetic_state_dict
 
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -102,9 +102,10 @@ class ImageTrainProcessor:
 class StarVectorStarCoder:
     """v1 model core (models/starvector_v1.py + starvector_base.py) bound to one Engine."""
 
-    def __init__(self, config: StarVectorConfig, engine: Engine, tokenizer, wte: torch.Tensor):
+    def __init__(self, config: StarVectorConfig, engine: Engine, tokenizer, wte: torch.Tensor, v2: bool = False):
         self.config = config
         self.engine = engine
+        self.v2 = v2                                                            # models/starvector_v2.py semantics
         self.task = "im2svg"
         self.query_length = engine.query_length
         self.max_length = config.max_length_train - self.query_length - 4      # starvector_base.py:41
@@ -156,7 +157,9 @@ class StarVectorStarCoder:
             max_new_tokens=int(max_new), do_sample=do_sample,
             temperature=float(kw.get("temperature", 1)), top_p=float(kw.get("top_p", 0.9)) if do_sample else 1.0,
             repetition_penalty=float(kw.get("repetition_penalty", 1.0)),
-            eos_token_id=self.eos_token_id, pad_token_id=tok.pad_token_id,
+            eos_token_id=self.eos_token_id,
+            # v1 passes tokenizer.pad_token_id (starvector_base.py:294); v2 passes nothing and HF falls back to eos
+            pad_token_id=(self.eos_token_id if self.v2 and self.eos_token_id is not None else tok.pad_token_id),
             stop_ids=kw.get("stop_ids", self._stop_ids()), stop_row0_only=True,
             seed=int(kw.get("seed", self.seed)),
         )
@@ -199,9 +202,11 @@ class StarVectorForCausalLM:
         self.dims = dims
         engine = Engine(dims, device)
         engine.load_state_dict(state_dict)
-        wte = state_dict[DEC + "wte.weight"].to(device=engine.device, dtype=torch.bfloat16)
+        v2 = dims.variant == 1
+        wte = state_dict[(DEC2 + "embed_tokens.weight") if v2 else (DEC + "wte.weight")].to(device=engine.device,
+                                                                                               dtype=torch.bfloat16)
         tok = load_tokenizer(tokenizer_path, dims.vocab)
-        self.model = StarVectorStarCoder(config, engine, tok, wte)
+        self.model = StarVectorStarCoder(config, engine, tok, wte, v2=v2)     # v2 = StarVectorStarCoder2 (starvector_arch.py:137-145)
         self.device = engine.device
         self.dtype = torch.bfloat16
 
@@ -215,6 +220,8 @@ class StarVectorForCausalLM:
         if dims is not None:
             config.engine_dims = {k: v for k, v in dims.__dict__.items() if k not in ("max_batch", "max_len")}
             max_batch, max_len = dims.max_batch, dims.max_len
+            if dims.variant == 1:
+                config.starcoder_model_name, config.image_encoder_type = "bigcode/starcoder2-7b", "siglip_384"
         d = config.to_dims(max_batch=max_batch, max_len=max_len)
         sd = state_dict if state_dict is not None else synthetic_state_dict(d, seed=seed, init=init)
         return cls(config, sd, device=device, max_batch=max_batch, max_len=max_len)

@@ -27,8 +27,73 @@ DEC = "model.svg_transformer.transformer.transformer."
 LM_HEAD = "model.svg_transformer.transformer.lm_head.weight"
 
 
+DEC2 = "model.svg_transformer.transformer.model."
+
+
+def weight_shapes_v2(d: ModelDims) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
+    """StarVector v2 (8B family) tensors: SiglipVisionTransformer keys (image_encoder.py:32-48; the pooling `head` is
+    omitted — the reference discards its output, image_encoder.py:109), Adapter, Starcoder2ForCausalLM keys
+    (llm/starcoder2.py:19-32)."""
+    W, Q, H = d.vit_width, d.query_length, d.hidden
+    kv, hq = d.n_kv_head * d.head_dim, d.n_head * d.head_dim
+    yield VIS + "embeddings.patch_embedding.weight", (W, 3, d.patch_size, d.patch_size), "conv"
+    yield VIS + "embeddings.patch_embedding.bias", (W,), "bias"
+    yield VIS + "embeddings.position_embedding.weight", (Q, W), "dec"
+    for i in range(d.vit_layers):
+        p = f"{VIS}encoder.layers.{i}."
+        yield p + "layer_norm1.weight", (W,), "ln_w"
+        yield p + "layer_norm1.bias", (W,), "ln_b"
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            yield p + f"self_attn.{n}.weight", (W, W), "linear"
+            yield p + f"self_attn.{n}.bias", (W,), "bias"
+        yield p + "layer_norm2.weight", (W,), "ln_w"
+        yield p + "layer_norm2.bias", (W,), "ln_b"
+        yield p + "mlp.fc1.weight", (d.vit_mlp, W), "linear"
+        yield p + "mlp.fc1.bias", (d.vit_mlp,), "bias"
+        yield p + "mlp.fc2.weight", (W, d.vit_mlp), "linear"
+        yield p + "mlp.fc2.bias", (W,), "bias"
+    yield VIS + "post_layernorm.weight", (W,), "ln_w"
+    yield VIS + "post_layernorm.bias", (W,), "ln_b"
+    yield ADP + "c_fc.weight", (2 * W, W), "xavier"
+    yield ADP + "c_fc.bias", (2 * W,), "bias"
+    yield ADP + "c_proj.weight", (H, 2 * W), "xavier"
+    yield ADP + "c_proj.bias", (H,), "bias"
+    if d.adapter_norm == 0:
+        yield ADP + "norm.weight", (Q, H), "ln_w"
+        yield ADP + "norm.bias", (Q, H), "ln_b"
+    else:
+        yield ADP + "norm.weight", (Q,), "ln_w"
+        yield ADP + "norm.bias", (Q,), "ln_b"
+        yield ADP + "norm.running_mean", (Q,), "bn_mean"
+        yield ADP + "norm.running_var", (Q,), "bn_var"
+    yield DEC2 + "embed_tokens.weight", (d.vocab, H), "dec"
+    for i in range(d.n_layer):
+        p = f"{DEC2}layers.{i}."
+        yield p + "input_layernorm.weight", (H,), "ln_w"
+        yield p + "input_layernorm.bias", (H,), "ln_b"
+        yield p + "self_attn.q_proj.weight", (hq, H), "dec"
+        yield p + "self_attn.q_proj.bias", (hq,), "bias"
+        yield p + "self_attn.k_proj.weight", (kv, H), "dec"
+        yield p + "self_attn.k_proj.bias", (kv,), "bias"
+        yield p + "self_attn.v_proj.weight", (kv, H), "dec"
+        yield p + "self_attn.v_proj.bias", (kv,), "bias"
+        yield p + "self_attn.o_proj.weight", (H, hq), "dec_proj"
+        yield p + "self_attn.o_proj.bias", (H,), "bias"
+        yield p + "post_attention_layernorm.weight", (H,), "ln_w"
+        yield p + "post_attention_layernorm.bias", (H,), "ln_b"
+        yield p + "mlp.c_fc.weight", (d.n_inner, H), "dec"
+        yield p + "mlp.c_fc.bias", (d.n_inner,), "bias"
+        yield p + "mlp.c_proj.weight", (H, d.n_inner), "dec_proj"
+        yield p + "mlp.c_proj.bias", (H,), "bias"
+    yield DEC2 + "norm.weight", (H,), "ln_w"
+    yield DEC2 + "norm.bias", (H,), "ln_b"
+
+
 def weight_shapes(d: ModelDims) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
     """Yield (name, shape, kind) for every tensor; kind drives the initialiser."""
+    if d.variant == 1:
+        yield from weight_shapes_v2(d)
+        return
     W, Q, H = d.vit_width, d.query_length, d.hidden
     kv = d.n_kv_head * d.head_dim
     yield VIS + "conv1.weight", (W, 3, d.patch_size, d.patch_size), "conv"
@@ -114,7 +179,7 @@ def synthetic_state_dict(
             t.uniform_(-b, b, generator=g)
         elif kind == "dec":
             t.normal_(0.0, 0.02, generator=g)
-            if name.endswith("wte.weight") and logit_gain != 1.0:
+            if (name.endswith("wte.weight") or name.endswith("embed_tokens.weight")) and logit_gain != 1.0:
                 t.mul_(logit_gain)
         elif kind == "dec_proj":
             t.normal_(0.0, 0.02 / math.sqrt(2 * d.n_layer), generator=g)
@@ -131,7 +196,7 @@ def synthetic_state_dict(
         else:  # pragma: no cover
             raise AssertionError(kind)
         sd[name] = t.to(dtype)
-    sd[LM_HEAD] = sd[DEC + "wte.weight"]
+    sd[LM_HEAD] = sd[(DEC2 + "embed_tokens.weight") if d.variant == 1 else (DEC + "wte.weight")]
     return sd
 
 

@@ -33,16 +33,18 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert C.sizeof(_lib.ModelDesc) == 19 * 4
+    assert C.sizeof(_lib.ModelDesc) == 22 * 4
     assert C.sizeof(_lib.GenParams) == 88 and _lib.GenParams.seed.offset == 72
 
 
 def test_create_rejects_bad_descriptors_without_touching_cuda():
     lib = _lib.load()
     h = C.c_void_p()
-    d = _lib.ModelDesc(variant=1)
+    d = _lib.ModelDesc(variant=7)
     assert lib.sv_engine_create(C.byref(d), 0, C.byref(h)) == _lib.SV_ERR_UNSUPPORTED
-    assert b"StarCoder2" in lib.sv_last_error(None)
+    d = _lib.ModelDesc(variant=1, rope_theta=0.0)
+    assert lib.sv_engine_create(C.byref(d), 0, C.byref(h)) == _lib.SV_ERR_INVALID
+    assert b"rope_theta" in lib.sv_last_error(None)
     d = _lib.ModelDesc(vit_width=100, vit_heads=2)
     assert lib.sv_engine_create(C.byref(d), 0, C.byref(h)) == _lib.SV_ERR_INVALID
 
@@ -77,8 +79,10 @@ def test_config_roundtrip_and_dims():
     c = StarVectorConfig()
     d = c.to_dims(max_batch=2, max_len=4096)
     assert (d.hidden, d.n_layer, d.vocab, d.max_len) == (2048, 24, 49156, 4096)
-    with pytest.raises(NotImplementedError):
-        StarVectorConfig(starcoder_model_name="bigcode/starcoder2-7b").to_dims()
+    d8 = StarVectorConfig(starcoder_model_name="bigcode/starcoder2-7b", image_encoder_type="siglip_384", image_size=384,
+                          hidden_size=4608, num_attention_heads=36, max_length=16384).to_dims(max_batch=2)
+    assert (d8.variant, d8.query_length, d8.hidden, d8.n_kv_head, d8.sliding_window) == (1, 576, 4608, 4, 4096)
+    assert d8.decoder_weight_bytes() == 14_347_893_760 and d8.kv_bytes_per_token() == 65_536
     c2 = StarVectorConfig(**{k: v for k, v in c.to_dict().items() if k not in ("model_type", "_name_or_path")})
     assert c2.hidden_size == c.hidden_size
 

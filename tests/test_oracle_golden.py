@@ -92,3 +92,22 @@ def test_restatement_bit_exact_vs_live_reference(golden_dir, norm):
         ref_v = ln(vt(img))
         assert torch.equal(ref_v, o.image_encoder(img))
         assert torch.equal(ad(ref_v), o.image_projection(ref_v))
+
+
+def test_v2_oracle_matches_fixture(golden_dir):
+    """v2 family (SigLIP + StarCoder2 from the installed transformers, reference Adapter): regression pin."""
+    from oracle.pipeline import OracleStarVectorV2
+
+    torch.set_num_threads(1)
+    g = torch.load(os.path.join(golden_dir, "tiny_v2_layer_norm.pt"), weights_only=False)
+    d = ModelDims(**g["dims"])
+    sd = synthetic_state_dict(d, seed=g["seed"], init=g["init"])
+    img = synthetic_images(d, 2, seed=g["image_seed"])
+    o = OracleStarVectorV2(d, sd, dtype=torch.float32)
+    vit = o.image_encoder(img.float())
+    torch.testing.assert_close(vit, g["vit_out_fp32"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(o.image_projection(vit), g["adapter_out_fp32"], rtol=1e-4, atol=1e-4)   # restated vs reference Adapter
+    n_new = g["greedy_ids_fp32"].shape[1] - 2
+    ids = o.generate_im2svg_ids(img, g["prompt_ids"], g["stop_ids"], use_nucleus_sampling=False, num_beams=1,
+                                max_length=d.query_length + 2 + n_new)
+    assert torch.equal(ids, g["greedy_ids_fp32"])

@@ -1,0 +1,99 @@
+"""StarVector v2 family (SigLIP tower + StarCoder2: GQA, RoPE, sliding window) — tiny-config parity vs the CPU oracle
+and the committed fixture (tests/golden/tiny_v2_layer_norm.pt, written by oracle/make_golden.py)."""
+import os
+
+import pytest
+import torch
+
+from oracle.pipeline import OracleStarVectorV2
+from starvector_b200.config import ModelDims
+from starvector_b200.engine import Engine, GenerationParams
+from starvector_b200.weights import synthetic_images, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _err(a, ref):
+    d = (a.float().cpu() - ref.float().cpu()).abs()
+    return d.max().item(), d.mean().item()
+
+
+def _as_accurate_as_bf16(engine_out, o16, o32, slack=2.0, floor=3e-2):
+    e_max, e_mean = _err(engine_out, o32)
+    o_max, o_mean = _err(o16, o32)
+    assert e_max <= slack * o_max + floor, f"max err {e_max:.4f} vs bf16-oracle {o_max:.4f}"
+    assert e_mean <= slack * o_mean + floor / 10, f"mean err {e_mean:.5f} vs bf16-oracle {o_mean:.5f}"
+
+
+@pytest.fixture(scope="module")
+def tiny_v2(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "tiny_v2_layer_norm.pt"), weights_only=False)
+    d = ModelDims(**g["dims"])
+    sd = synthetic_state_dict(d, seed=g["seed"], init=g["init"])
+    eng = Engine(d, 0)
+    eng.load_state_dict(sd)
+    img = synthetic_images(d, 2, seed=g["image_seed"])
+    yield g, d, sd, eng, img
+    eng.close()
+
+
+def test_v2_vision_and_adapter(tiny_v2):
+    g, d, sd, eng, img = tiny_v2
+    emb, vit = eng.encode_images(img, return_embeds=True, return_vit=True)
+    assert vit.shape == (2, d.query_length, d.vit_width) and d.query_length == (d.image_size // d.patch_size) ** 2
+    _as_accurate_as_bf16(vit, g["vit_out_bf16"], g["vit_out_fp32"])
+    _as_accurate_as_bf16(emb, g["adapter_out_bf16"], g["adapter_out_fp32"])
+
+
+def test_v2_teacher_forced_logits_cross_the_sliding_window(tiny_v2):
+    g, d, sd, eng, img = tiny_v2
+    forced = g["forced_ids"]
+    assert d.query_length + 2 + forced.shape[1] > d.sliding_window + 8
+    eng.encode_images(img)
+    logits = [eng.prefill(torch.tensor([g["prompt_ids"]] * 2), return_logits=True)]
+    for j in range(forced.shape[1]):
+        logits.append(eng.decode_step(forced[:, j]))
+    got = torch.stack(logits, dim=1)
+    _as_accurate_as_bf16(got, g["tf_logits_bf16"], g["tf_logits_fp32"], floor=4e-2)
+
+
+def test_v2_greedy_ids(tiny_v2):
+    g, d, sd, eng, img = tiny_v2
+    ref = g["greedy_ids_bf16"][:, len(g["prompt_ids"]):]
+    ref_logits = g["greedy_logits_bf16"]
+    eng.encode_images(img)
+    eng.prefill(torch.tensor([g["prompt_ids"]] * 2))
+    got = eng.generate(GenerationParams(max_new_tokens=ref.shape[1], eos_token_id=0, pad_token_id=0,
+                                        stop_ids=g["stop_ids"])).cpu().long()
+    assert got.shape == ref.shape
+    for b in range(2):
+        for s in range(ref.shape[1]):
+            if got[b, s] != ref[b, s]:
+                top2 = ref_logits[s, b].topk(2).values
+                assert (top2[0] - top2[1]).item() < 0.05, f"row {b} step {s}: ids differ at oracle margin {(top2[0]-top2[1]).item():.4f}"
+                break
+
+
+def test_v2_against_live_oracle_random_walk(tiny_v2):
+    """Un-tied random head -> non-degenerate greedy walk through RoPE + GQA + window."""
+    g, d, sd, eng, img = tiny_v2
+    sd2 = dict(sd)
+    gen = torch.Generator().manual_seed(5)
+    sd2["model.svg_transformer.transformer.lm_head.weight"] = (torch.randn(d.vocab, d.hidden, generator=gen) * 0.2).to(torch.bfloat16)
+    e2 = Engine(d, 0)
+    e2.load_state_dict(sd2)
+    o = OracleStarVectorV2(d, sd2, dtype=torch.bfloat16)
+    ref, ref_logits = o.generate_im2svg_ids(img, g["prompt_ids"], (), return_logits=True, use_nucleus_sampling=False,
+                                            num_beams=1, max_length=d.query_length + 2 + 36)
+    ref = ref[:, 2:]
+    e2.encode_images(img)
+    e2.prefill(torch.tensor([g["prompt_ids"]] * 2))
+    got = e2.generate(GenerationParams(max_new_tokens=36, eos_token_id=0, pad_token_id=0)).cpu().long()
+    e2.close()
+    assert len(set(ref[0].tolist())) > 4
+    for b in range(2):
+        for s in range(ref.shape[1]):
+            if got[b, s] != ref[b, s]:
+                top2 = ref_logits[s, b].topk(2).values
+                assert (top2[0] - top2[1]).item() < 0.05, f"row {b} step {s}: margin {(top2[0]-top2[1]).item():.4f}"
+                break
