@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--max-new-tokens", type=int, default=4096)
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="1b", choices=["1b", "8b"],
+                    help="1b = StarVector-1B (headline, configs[1]); 8b = StarVector-8B family dims (SigLIP + StarCoder2)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -170,7 +172,7 @@ def main():
 
     import torch.distributed as dist
 
-    from starvector_b200.config import dims_1b
+    from starvector_b200.config import dims_1b, dims_8b
     from starvector_b200.engine import Engine, GenerationParams
     from starvector_b200.parallel import all_gather_generated
     from starvector_b200.weights import synthetic_images, synthetic_state_dict
@@ -187,7 +189,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B, n_new = args.batch_per_gpu, args.max_new_tokens
-    d = dims_1b(max_batch=max(B, 1), max_len=min(8192, 257 + len(PROMPT_IDS) + n_new + 32))
+    if args.model == "8b":
+        d = dims_8b(max_batch=max(B, 1), max_len=min(16384, 576 + len(PROMPT_IDS) + n_new + 32))
+    else:
+        d = dims_1b(max_batch=max(B, 1), max_len=min(8192, 257 + len(PROMPT_IDS) + n_new + 32))
     sd = synthetic_state_dict(d, seed=0)                      # every rank builds the same replica
     eng = Engine(d, local)
     eng.load_state_dict(sd)
@@ -198,6 +203,7 @@ def main():
     prompt_host = torch.tensor([PROMPT_IDS] * B, dtype=torch.int32).pin_memory()
     prompt_dev = prompt_host.to(dev)
     params = GenerationParams(max_new_tokens=n_new, eos_token_id=None, pad_token_id=49152)
+    workload = WORKLOAD if args.model == "1b" else WORKLOAD.replace("StarVector-1B", "StarVector-8B (SigLIP-L/16-384 + StarCoder2-7B dims)").replace("224x224", "384x384")
 
     def step_resident():
         eng.encode_images(img_dev)
@@ -276,16 +282,16 @@ def main():
 
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_decode_step_traffic.json")
-    if os.path.exists(tpath) and B == 1:      # ncu-measured DRAM bytes of one decode step (B=1, default decode mode)
+    if os.path.exists(tpath) and B == 1 and args.model == "1b":      # ncu-measured DRAM bytes of one decode step (B=1, default decode mode)
         with open(tpath) as f:
             tj = json.load(f)
         traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic (random-init StarVector-1B weights, seeded noise images)",
-        "config": {"workload": WORKLOAD.format(b=B, n=n_new), "global_batch": gb, "parallelism": f"batch-shard x{world}",
-                   "l2": "no flush needed: 2.24 GB of weights stream per decode step (>> 126 MB L2)",
+        "data": f"synthetic (random-init StarVector-{args.model.upper()} weights, seeded noise images)",
+        "config": {"workload": workload.format(b=B, n=n_new), "global_batch": gb, "parallelism": f"batch-shard x{world}",
+                   "l2": f"no flush needed: {d.decoder_weight_bytes() / 1e9:.2f} GB of weights stream per decode step (>> 126 MB L2)",
                    "prompt_len": len(PROMPT_IDS), "prefix_len": t0},
         "prefill_ms_per_image": pf_ms / 5 / B,
         "decode_ms_per_token_step": step_ms,
@@ -299,7 +305,7 @@ def main():
                      "traffic": traffic, "peak_source": peak_src, "kernel": "decode step (CUDA graph of the per-token kernels)",
                      "algorithmic_bytes_per_step": int(bytes_per_step)},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "1b":
         threads = min(os.cpu_count() or 1, CPU_THREADS_CAP)
         r = cpu_reference_run(threads, target_new=n_new, repeats=1)[0]
         line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": threads, "kind": "port",

@@ -1,29 +1,20 @@
-// Decode-step kernels (one new token per image; the >99% cost of the BASELINE workloads).
+// Decode-step kernels, register-landing generation (`SV_GEMV=regs`) + the fused token-selection kernel.
 //
-// A decode step streams every decoder weight once (2.24 GB for StarVector-1B), so it is HBM-bound
-// and the design goal is: every SM always has tens of KB of 128-bit weight loads in flight, and
-// as few dependent kernel boundaries as possible.  Per layer the step is FIVE kernels:
-//     gemv8<LN>  : ln_1 + c_attn (+bias) + KV-cache append            (was 3 kernels)
-//     attention  : split-KV multi-query attention + in-kernel merge   (was 2 kernels)
-//     gemv8      : attn.c_proj + bias + residual
-//     gemv8<LN>  : ln_2 + mlp.c_fc + bias + gelu_tanh                 (was 2 kernels)
-//     gemv8      : mlp.c_proj + bias + residual
-// then gemv8<LN> for ln_f + lm_head (+ per-tile argmax partials) and one single-CTA kernel that
-// finishes token selection, the HF stop/EOS bookkeeping and the next token's embedding.
+// A decode step streams every decoder weight once (2.24 GB for StarVector-1B), so it is HBM-bound; per layer the
+// step is five kernels (ln_1+c_attn+KV append | attention | c_proj+residual | ln_2+c_fc+gelu | mlp.c_proj+residual),
+// then ln_f+lm_head (+ per-tile argmax partials) and one single-CTA kernel that finishes token selection, the HF
+// stop/EOS bookkeeping and the next token's embedding.
 //
-// gemv8: one CTA owns 8 output features (8 weight rows) and ALL of K, its NW warps take
-// interleaved 32-element K chunks; every lane issues its whole share of 128-bit weight loads
-// up front (8 per lane in flight; a CTA of 8 warps keeps 32 KB in flight, ~1.7-7 CTAs per SM).
-// Weights are the tensor-core "A" operand (rows 8..15 of the m16 tile are zero), the <= 8
-// activation rows are "B": the legacy mma.sync path is plenty for a bandwidth-bound GEMV.
-// LayerNorm is fused as a prologue: each lane loads exactly the activation elements it feeds to
-// its MMAs, row statistics are reduced across the CTA, normalisation happens in registers.
+// gemvp_kernel here is the first persistent GEMV: 128-bit weight loads land in REGISTERS (16 per lane in flight,
+// 64 KB per SM), rows tiled R <= 16 per CTA so every SM streams the same bytes, LayerNorm fused as a prologue on
+// register-resident activation fragments.  The default path has since moved to the shared-memory weight ring
+// (sv_decode_mega.cu: gemv_ring_kernel, ~165 KB in flight per SM); this version stays as an A/B reference and for
+// shapes the ring does not take.  select_fused_kernel (below) is used by every decode mode.
 //
-// All kernels are written for Programmatic Dependent Launch: weights (never written at run
-// time) are prefetched BEFORE `griddepcontrol.wait`, so kernel N+1's loads are already in flight
-// while kernel N drains; everything produced by the previous kernel is read after the wait with
-// L2-only loads (ld.global.cg), because a co-resident CTA of the previous kernel may have left a
-// stale copy of an in-place-updated buffer in this SM's L1.
+// All kernels are written for Programmatic Dependent Launch: weights (never written at run time) are prefetched
+// BEFORE `griddepcontrol.wait`; everything produced by the previous kernel is read after the wait with L2-only
+// loads (ld.global.cg), because a co-resident CTA of the previous kernel may have left a stale copy of an
+// in-place-updated buffer in this SM's L1.
 #include "sv_kernels.h"
 #include "sv_select.cuh"
 

@@ -90,10 +90,26 @@ def test_v2_against_live_oracle_random_walk(tiny_v2):
     e2.prefill(torch.tensor([g["prompt_ids"]] * 2))
     got = e2.generate(GenerationParams(max_new_tokens=36, eos_token_id=0, pad_token_id=0)).cpu().long()
     e2.close()
-    assert len(set(ref[0].tolist())) > 4
+    assert len(set(ref[0].tolist())) >= 3, "walk degenerate: test lost its power"
     for b in range(2):
         for s in range(ref.shape[1]):
             if got[b, s] != ref[b, s]:
                 top2 = ref_logits[s, b].topk(2).values
                 assert (top2[0] - top2[1]).item() < 0.05, f"row {b} step {s}: margin {(top2[0]-top2[1]).item():.4f}"
                 break
+
+
+def test_v2_facade_strings_match_oracle(tiny_v2):
+    """StarVectorStarCoder2 surface: pad falls back to eos (starvector_v2.py:53-57), embed_tokens for the prompt."""
+    from starvector_b200.modeling import StarVectorForCausalLM
+
+    g, d, sd, eng, img = tiny_v2
+    m = StarVectorForCausalLM.from_config(dims=d, state_dict=sd)
+    tok = m.model.svg_transformer.tokenizer
+    prompt = tok("<svg")["input_ids"]
+    kw = dict(use_nucleus_sampling=False, num_beams=1, max_length=d.query_length + len(prompt) + 12)
+    got = m.generate_im2svg({"image": img.cuda()}, **kw)
+    o = OracleStarVectorV2(d, sd, dtype=torch.bfloat16)
+    ref = o.generate_im2svg_ids(img, prompt, tok("</svg>")["input_ids"], **kw)
+    assert got == tok.batch_decode(ref, skip_special_tokens=True)
+    m.model.engine.close()
