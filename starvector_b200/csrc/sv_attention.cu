@@ -472,7 +472,8 @@ SV_DEVINL float ld_dsmem(uint32_t local_addr, uint32_t cta_rank) {
 template <int D>
 __global__ void __launch_bounds__(kDecWarps * 32, 1) attention_decode_cluster_kernel(
     const bf16* __restrict__ qkv, int ld, const bf16* __restrict__ kcache, const bf16* __restrict__ vtcache,
-    bf16* __restrict__ out, const GenState* __restrict__ state, int n_head, int n_kv, int tcap, float scale_log2) {
+    bf16* __restrict__ out, const GenState* __restrict__ state, int n_head, int n_kv, int tcap, float scale_log2,
+    int window) {
   extern __shared__ float dsm[];                               // [kDecWarps][PSZ] warp partials | [PSZ] CTA partial
   constexpr int PSZ = 32 + 16 * D;
   float* cta_part = dsm + kDecWarps * PSZ;
@@ -482,9 +483,10 @@ __global__ void __launch_bounds__(kDecWarps * 32, 1) attention_decode_cluster_ke
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int cta = blockIdx.x, ncta = gridDim.x, kvh = blockIdx.y, b = blockIdx.z;
   const int group = n_head / n_kv;
-  const int blocks = (nkeys + 31) / 32;
-  const int per = (blocks + ncta - 1) / ncta;
-  const int blk0 = cta * per, blk1 = min(blocks, blk0 + per);
+  const int key_lo = window > 0 ? max(0, nkeys - window) : 0;    // sliding window (StarCoder2): keys in (q - window, q]
+  const int blk_lo = key_lo / 32, blk_hi = (nkeys + 31) / 32;
+  const int per = (blk_hi - blk_lo + ncta - 1) / ncta;
+  const int blk0 = blk_lo + cta * per, blk1 = min(blk_hi, blk0 + per);
   const int64_t bk = (int64_t)b * n_kv + kvh;
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 1) attention_decode_cluster_ke
     load_q_frag<D, true>(qa, qrow + (int64_t)g * D, g < group, qrow + (int64_t)(g + 8) * D, g + 8 < group, t);
     for (int blk = blk0 + warp; blk < blk1; blk += kDecWarps)
       attn_core<D, true, true>(qa, kcache + bk * tcap * D, D, vtcache + bk * D * tcap, tcap, blk * 32,
-                         min(nkeys, blk * 32 + 32), scale_log2, acc, mrow, lrow, lane);
+                               min(nkeys, blk * 32 + 32), scale_log2, acc, mrow, lrow, lane, key_lo);
   }
   float* ws = dsm + warp * PSZ;
   const float l0 = quad_sum(lrow[0]), l1 = quad_sum(lrow[1]);
@@ -565,7 +567,7 @@ cudaError_t attention_decode_cluster_init() {
 
 cudaError_t launch_attention_decode_cluster(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache,
                                             bf16* out, const GenState* state, int batch, int n_head, int n_kv, int d,
-                                            int tcap, int ncta, bool pdl, cudaStream_t st) {
+                                            int tcap, int ncta, int window, bool pdl, cudaStream_t st) {
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ncta, n_kv, batch); cfg.blockDim = dim3(kDecWarps * 32);
@@ -577,7 +579,7 @@ cudaError_t launch_attention_decode_cluster(const bf16* qkv, int q_cols_total, c
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, attention_decode_cluster_kernel<128>, qkv, q_cols_total, kcache, vtcache, out,
-                                     state, n_head, n_kv, tcap, scale_log2);
+                                     state, n_head, n_kv, tcap, scale_log2, window);
   count_launch();
   return e;
 }

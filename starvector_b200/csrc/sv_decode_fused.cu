@@ -357,9 +357,11 @@ __global__ void __launch_bounds__(1024) select_fused_kernel(const bf16* __restri
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
     float e[8], q[8];
     unpack8(ldg_cached(wte + (int64_t)id * h + c), e);
-    unpack8(ldg_cached(wpe + (int64_t)pos * h + c), q);
+    if (wpe) {                                                  // RoPE models have no learned position table
+      unpack8(ldg_cached(wpe + (int64_t)pos * h + c), q);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) e[j] += q[j];
+      for (int j = 0; j < 8; ++j) e[j] += q[j];
+    }
     *reinterpret_cast<uint4*>(x + (int64_t)b * h + c) = pack8(e);
   }
 }

@@ -116,7 +116,9 @@ SV_DEVINL Plan make_plan(int N, int K, int cta, int ncta) {
   p.ntiles = (N + p.R - 1) / p.R;
   p.tile0 = cta * p.tpc;
   p.ntile = max(0, min(p.tpc, p.ntiles - p.tile0));
-  p.KS = K < KS_MAX ? K : KS_MAX;
+  // slab width: the largest of {1024, 768, 512, 256, 128, 64, 32} that divides K (4608 -> 768, 18432 -> 1024)
+  p.KS = 32;
+  for (int ks : {1024, 768, 512, 256, 128, 64}) if (ks <= K && K % ks == 0) { p.KS = ks; break; }
   p.nstg = K / p.KS;
   p.pitch = p.KS * 2 + 64;
   return p;
@@ -178,7 +180,9 @@ struct Ctx {
 };
 
 // ---- consumer: one GEMV phase  Y[B,N] = epi( LN?(X)[B,K] . W[N,K]^T )
-template <bool HAS_LN, int EPI>
+// LN_BIGK compiles in the LayerNorm path for K > 2048 (v2); v1 kernels are instantiated without it so their register
+// allocation is untouched.
+template <bool HAS_LN, int EPI, bool LN_BIGK = false>
 SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, const bf16* __restrict__ bias,
                           const bf16* res, bf16* Y, int N, int K, int act, const bf16* __restrict__ ln_w,
                           const bf16* __restrict__ ln_b, const Layer* L) {
@@ -263,6 +267,54 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
     }
   }
 
+  // LayerNorm with K > 2048 (StarCoder2: H = 4608): row statistics in two streaming passes over x (L2 resident),
+  // the normalisation itself happens per slab inside the MMA loop.
+  float ln_mean = 0.f, ln_rstd = 1.f;
+  if constexpr (HAS_LN && LN_BIGK) {
+    if (big_k && p.ntile > 0) {
+      float sv = 0.f;
+      for (int ks = 0; ks < p.nstg; ++ks) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cl = warp + NWC * j;
+          if (row_ok && j < cpws && cl < cps) {
+            float f[8];
+            unpack8(ldcg16(xp + (ks * cps + cl) * 32), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sv += f[e];
+          }
+        }
+      }
+      sv = quad_sum(sv);
+      if (t == 0) cx.stat[warp * 8 + g] = sv;
+      consumer_sync();
+#pragma unroll
+      for (int w = 0; w < NWC; ++w) ln_mean += cx.stat[w * 8 + g];
+      ln_mean /= (float)K;
+      float q = 0.f;
+      for (int ks = 0; ks < p.nstg; ++ks) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cl = warp + NWC * j;
+          if (row_ok && j < cpws && cl < cps) {
+            float f[8];
+            unpack8(ldcg16(xp + (ks * cps + cl) * 32), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float dlt = f[e] - ln_mean; q += dlt * dlt; }
+          }
+        }
+      }
+      q = quad_sum(q);
+      consumer_sync();
+      if (t == 0) cx.stat[warp * 8 + g] = q;
+      consumer_sync();
+      float var = 0.f;
+#pragma unroll
+      for (int w = 0; w < NWC; ++w) var += cx.stat[w * 8 + g];
+      ln_rstd = 1.0f / sqrtf(var / (float)K + a.ln_eps);
+    }
+  }
+
   float c[4] = {0.f, 0.f, 0.f, 0.f};
   for (int tl = 0; tl < p.ntile; ++tl) {
     const int tile = p.tile0 + tl;
@@ -288,20 +340,42 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
         }
       }
     } else {
-      // K > 2048: activation fragments are fetched per slot from L2, one slot ahead of their use
-      uint4 xc[4], xn[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cl = warp + NWC * j;
-        xc[j] = (row_ok && j < cpws && cl < cps) ? ldcg16(xp + cl * 32) : make_uint4(0u, 0u, 0u, 0u);
-      }
-      for (int ks = 0; ks < p.nstg; ++ks) {
+      // K > 2048: activation fragments are fetched per slab from L2, one slab ahead of their use (with HAS_LN the
+      // LayerNorm affine of the same columns rides along and the fragment is normalised after the slab's MMAs).
+      constexpr bool LNB = HAS_LN && LN_BIGK;
+      uint4 xc[4], xn[4], wn[LNB ? 4 : 1], bn[LNB ? 4 : 1];
+      auto fetch = [&](int ks) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int cl = warp + NWC * j;
-          xn[j] = (row_ok && ks + 1 < p.nstg && j < cpws && cl < cps) ? ldcg16(xp + ((ks + 1) * cps + cl) * 32)
-                                                                       : make_uint4(0u, 0u, 0u, 0u);
+          const bool okc = ks < p.nstg && j < cpws && cl < cps;
+          const int ch = okc ? ks * cps + cl : 0;
+          xn[j] = (row_ok && okc) ? ldcg16(xp + ch * 32) : make_uint4(0u, 0u, 0u, 0u);
+          if constexpr (LNB) {
+            wn[j] = okc ? ldg_cached(ln_w + ch * 32 + 8 * t) : make_uint4(0u, 0u, 0u, 0u);
+            bn[j] = okc ? ldg_cached(ln_b + ch * 32 + 8 * t) : make_uint4(0u, 0u, 0u, 0u);
+          }
         }
+      };
+      auto promote = [&](int ks) {             // xn (raw) -> xc (what the MMAs consume)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (LNB) {
+            const bool okc = ks < p.nstg && j < cpws && (warp + NWC * j) < cps;
+            float f[8], wf[8], bfv[8];
+            unpack8(xn[j], f); unpack8(wn[j], wf); unpack8(bn[j], bfv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = (row_ok && okc) ? (f[e] - ln_mean) * ln_rstd * wf[e] + bfv[e] : 0.f;
+            xc[j] = pack8(f);
+          } else {
+            xc[j] = xn[j];
+          }
+        }
+      };
+      fetch(0);
+      promote(0);
+      for (int ks = 0; ks < p.nstg; ++ks) {
+        fetch(ks + 1);
         mbar_wait(r.full0 + 8u * r.slot, r.phase);
         const uint32_t sb = r.base + r.slot * SLOT_BYTES + g * p.pitch + t * 16;
 #pragma unroll
@@ -316,8 +390,7 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
         __syncwarp();
         if (cx.lane == 0) mbar_arrive(r.empty0 + 8u * r.slot);
         r.advance();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) xc[j] = xn[j];
+        promote(ks + 1);
       }
     }
     // ---- tile finished: deterministic cross-warp split-K reduction + epilogue
@@ -699,7 +772,7 @@ SV_DEVINL void l2_prefetch_share(const void* base, unsigned long long bytes, int
 SV_DEVINL constexpr int ring_smem_bytes(int nslots) { return nslots * SLOT_BYTES + RED_BYTES + NWC * 8 * 4 + 2 * 8 * 8 + 256; }
 
 // (A 2-CTA/SM register budget (96 regs) so that consecutive kernels co-reside under PDL was measured 25% slower.)
-template <bool HAS_LN, int EPI>
+template <bool HAS_LN, int EPI, bool LN_BIGK = false>
 __global__ void __launch_bounds__(NTHREADS, 1) gemv_ring_kernel(const RingGemvArgs ra) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -727,7 +800,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_ring_kernel(const RingGemvAr
   cx.a = &ra.a; cx.smem = smem; cx.cta = cta; cx.ncta = ncta; cx.warp = warp; cx.lane = lane; cx.g = lane >> 2; cx.t = lane & 3;
   cx.red = reinterpret_cast<float*>(smem + off_red);
   cx.stat = reinterpret_cast<float*>(smem + off_stat);
-  gemv_phase<HAS_LN, EPI>(cx, ring, ra.X, ra.bias, ra.res, ra.Y, ra.N, ra.K, ra.act, ra.ln_w, ra.ln_b, &ra.L);
+  gemv_phase<HAS_LN, EPI, LN_BIGK>(cx, ring, ra.X, ra.bias, ra.res, ra.Y, ra.N, ra.K, ra.act, ra.ln_w, ra.ln_b, &ra.L);
 }
 
 }  // namespace mega
@@ -779,7 +852,7 @@ cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st) {
 
 
 // ---- per-phase ring GEMV launchers (used by the CUDA-graph decode path)
-template <bool HAS_LN, int EPI>
+template <bool HAS_LN, int EPI, bool LN_BIGK = false>
 static void launch_ring_t(const mega::RingGemvArgs& ra, int ncta, bool pdl, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(mega::NTHREADS); cfg.stream = st;
@@ -788,7 +861,7 @@ static void launch_ring_t(const mega::RingGemvArgs& ra, int ncta, bool pdl, cuda
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, mega::gemv_ring_kernel<HAS_LN, EPI>, ra);
+  cudaLaunchKernelEx(&cfg, mega::gemv_ring_kernel<HAS_LN, EPI, LN_BIGK>, ra);
   count_launch();
 }
 
@@ -800,13 +873,14 @@ cudaError_t gemv_ring_init() {   // set the shared-memory opt-in outside of any 
   SV_RING_ATTR(true, mega::EPI_QKV) SV_RING_ATTR(true, mega::EPI_PLAIN) SV_RING_ATTR(true, mega::EPI_LMHEAD)
   SV_RING_ATTR(false, mega::EPI_PLAIN)
 #undef SV_RING_ATTR
+  e = cudaFuncSetAttribute(mega::gemv_ring_kernel<true, mega::EPI_PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(mega::gemv_ring_kernel<true, mega::EPI_LMHEAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   return cudaSuccess;
 }
 
-bool gemv_ring_supported(int K, bool has_ln) {
-  const bool okk = K % 32 == 0 && (K <= mega::KS_MAX || K % mega::KS_MAX == 0);
-  return okk && (!has_ln || K <= 2 * mega::KS_MAX);
-}
+bool gemv_ring_supported(int K, bool has_ln) { (void)has_ln; return K >= 32 && K % 32 == 0; }
 
 int gemv_ring_ntiles(int N) {
   int dev = 0, nsm = 148;
@@ -831,11 +905,18 @@ void launch_gemv_ring(const RingGemvLaunch& g, cudaStream_t st) {
     static int cap = 0;
     if (cap == 0) { const char* c = getenv("SV_RING_SLOTS"); cap = c ? atoi(c) : 5; if (cap < 1 || cap > 6) cap = 5; }
     const int rows_per_cta = (g.N + nsm - 1) / nsm, tpc = (rows_per_cta + 15) / 16;
-    const int ks = g.K < mega::KS_MAX ? g.K : mega::KS_MAX, need = tpc * (g.K / ks);
+    int ks = 32;
+    for (int c : {1024, 768, 512, 256, 128, 64}) if (c <= g.K && g.K % c == 0) { ks = c; break; }
+    const int need = tpc * (g.K / ks);
     ra.nslots = need < cap ? need : cap;
     if (ra.nslots < 1) ra.nslots = 1;
   }
   const bool ln = g.ln_w != nullptr;
+  if (ln && g.K > 2 * mega::KS_MAX) {       // LayerNorm over K > 2048 (v2): separate instantiations
+    if (g.epi == mega::EPI_LMHEAD) launch_ring_t<true, mega::EPI_LMHEAD, true>(ra, nsm, g.pdl, st);
+    else launch_ring_t<true, mega::EPI_PLAIN, true>(ra, nsm, g.pdl, st);
+    return;
+  }
   if (ln && g.epi == mega::EPI_QKV) launch_ring_t<true, mega::EPI_QKV>(ra, nsm, g.pdl, st);
   else if (ln && g.epi == mega::EPI_LMHEAD) launch_ring_t<true, mega::EPI_LMHEAD>(ra, nsm, g.pdl, st);
   else if (ln) launch_ring_t<true, mega::EPI_PLAIN>(ra, nsm, g.pdl, st);

@@ -441,9 +441,9 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
   if (ids) launch_embed_tokens(ids, e->wte, e->wpe, e->state, e->d_x, B, H, d.vocab, d.n_positions, st);
   bool first = true;
   auto attention = [&](bf16* kc, bf16* vc) {
-    if (e->use_cluster_attn)
+    if (e->use_cluster_attn || e->v2)
       launch_attention_decode_cluster(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->state, B, d.n_head, d.n_kv_head, D,
-                                      e->tcap, std::min(ncta, 8), pdl, st);
+                                      e->tcap, std::min(ncta, 8), e->window, pdl, st);
     else
       launch_attention_decode_fused(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->attn_partial, e->attn_counters,
                                     e->state, B, d.n_head, d.n_kv_head, D, e->tcap, ncta, pdl, st);
@@ -478,9 +478,12 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
       const bool last = i + 1 == d.n_layer;
       const bf16* next_first = last ? e->lm_head : e->dec[i + 1].attn_w;       // what follows this layer's mlp.c_proj
       which = 0;
-      gemv(e->d_x, L.attn_w, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, 1, kc, vc,
-           pdl && !first, L.proj_w, n_proj);
+      gemv(e->d_x, L.attn_w, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, e->v2 ? 0 : 1, kc,
+           vc, pdl && !first, L.proj_w, n_proj);
       first = false;
+      if (e->v2)   // RoPE on q,k then append (the GEMV epilogue cannot rotate: the pair element lives in another tile)
+        launch_rope_append(e->d_qkv, B, e->qkv_cols, d.n_head, d.n_kv_head, D, e->rope_cos, e->rope_sin, kc, vc, e->state,
+                           e->tcap, d.n_positions, pdl, st);
       attention(kc, vc);
       which = 1;
       gemv(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, H, H, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl,
@@ -615,8 +618,6 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   if (dec && !strcmp(dec, "legacy")) e->fused_decode = false;
   const char* pdl = getenv("SV_PDL");             // "0" = plain stream order between decode kernels
   if (pdl && !strcmp(pdl, "0")) e->use_pdl = false;
-  if (!gemv8_supported(d.hidden, true) || !gemv8_supported(d.n_inner, false)) e->fused_decode = false;
-  if (e->v2) e->fused_decode = false;             // v2 decodes on the per-op kernels (+RoPE, sliding window) this round
   const char* mg = getenv("SV_MEGA");             // "1" = persistent multi-token kernel instead of the per-phase CUDA graph
   e->use_mega = mg && !strcmp(mg, "1");           // (opt-in until it beats the graph path: DESIGN.md "decode modes")
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
@@ -627,6 +628,13 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   const char* rg = getenv("SV_GEMV");             // "regs" = register-landing GEMV kernels instead of the smem weight ring
   if (rg && !strcmp(rg, "regs")) e->use_ring = false;
   if (!gemv_ring_supported(d.hidden, true) || !gemv_ring_supported(d.n_inner, false)) e->use_ring = false;
+  // the fused step needs one of the two GEMV generations to take these widths; v2 (RoPE, K = 4608) only runs on the ring
+  const bool regs_ok = !e->v2 && gemv8_supported(d.hidden, true) && gemv8_supported(d.n_inner, false);
+  if (!e->use_ring && !regs_ok) e->fused_decode = false;
+  if (e->v2) e->use_cluster_attn = true;          // the ticket kernel has no sliding-window support
+  // v2 at full size: the per-op kernels measure faster (4.4 vs 5.8 ms/token at 8B; 768-wide slabs + per-slab LayerNorm
+  // on the consumer path), so the fused ring step is opt-in for v2 (SV_DECODE=fused) until that is fixed.
+  if (e->v2 && !(dec && !strcmp(dec, "fused"))) e->fused_decode = false;
   if (!build_weights(e) || !build_buffers(e)) {
     std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     sv_engine_destroy(e);

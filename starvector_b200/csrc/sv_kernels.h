@@ -81,6 +81,9 @@ void launch_attention_decode(const bf16* qkv, int q_cols_total, const bf16* kcac
 // cos/sin tables are bf16 [max_pos][D/2]; position of row r = pos0 + (r % seq) or state->cur_len when state != nullptr.
 void launch_rope(bf16* qkv, int rows, int seq, int qkv_cols, int n_rot_heads, int d, const bf16* cos_t, const bf16* sin_t,
                  const GenState* state, int max_pos, cudaStream_t st);
+void launch_rope_append(bf16* qkv, int batch, int qkv_cols, int n_head, int n_kv, int d, const bf16* cos_t,
+                        const bf16* sin_t, bf16* kcache, bf16* vtcache, const GenState* state, int tcap, int max_pos,
+                        bool pdl, cudaStream_t st);
 void launch_rope_table(bf16* cos_t, bf16* sin_t, int max_pos, int d, float theta, cudaStream_t st);
 
 // fused decode attention (PDL-ready): ncta from attention_decode_fused_ncta(max total length)
@@ -95,7 +98,7 @@ int attention_decode_cluster_ncta(int total_len);
 cudaError_t attention_decode_cluster_init();
 cudaError_t launch_attention_decode_cluster(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache,
                                             bf16* out, const GenState* state, int batch, int n_head, int n_kv, int d,
-                                            int tcap, int ncta, bool pdl, cudaStream_t st);
+                                            int tcap, int ncta, int window, bool pdl, cudaStream_t st);
 
 // ---- sv_decode_fused.cu : decode-step GEMVs with fused LayerNorm / KV append / argmax, PDL-ready
 bool gemv8_supported(int K, bool has_ln);

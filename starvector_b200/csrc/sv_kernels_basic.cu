@@ -570,6 +570,55 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, int seq, int qkv_cols, int n
     v[j + half] = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
   }
 }
+// Decode-step companion of the fused QKV GEMV for RoPE models: rotate q in place, rotate k and append it (and v) to the
+// KV cache at position cur_len.  One block per image.
+__global__ void rope_append_kernel(bf16* __restrict__ qkv, int qkv_cols, int n_head, int n_kv, int d,
+                                   const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+                                   bf16* __restrict__ kcache, bf16* __restrict__ vtcache,
+                                   const GenState* __restrict__ state, int tcap, int max_pos) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int b = blockIdx.x, half = d >> 1;
+  const int pos = state->cur_len;
+  const int tp = pos >= max_pos ? max_pos - 1 : pos;
+  bf16* base = qkv + (int64_t)b * qkv_cols;
+  for (int i = threadIdx.x; i < (n_head + n_kv) * half; i += blockDim.x) {
+    const int h = i / half, j = i % half;
+    bf16* v = base + h * d;
+    const float c = __bfloat162float(cos_t[(int64_t)tp * half + j]), s = __bfloat162float(sin_t[(int64_t)tp * half + j]);
+    const float x1 = __bfloat162float(__ldcg(v + j)), x2 = __bfloat162float(__ldcg(v + j + half));
+    const bf16 o1 = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * s));
+    const bf16 o2 = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
+    if (h < n_head) {
+      v[j] = o1; v[j + half] = o2;
+    } else if (pos < tcap) {
+      const int kvh = h - n_head;
+      bf16* kr = kcache + (((int64_t)b * n_kv + kvh) * tcap + pos) * d;
+      kr[j] = o1; kr[j + half] = o2;
+    }
+  }
+  if (pos < tcap) {
+    const bf16* vsrc = base + (n_head + n_kv) * d;
+    for (int i = threadIdx.x; i < n_kv * d; i += blockDim.x) {
+      const int kvh = i / d, dim = i % d;
+      vtcache[(((int64_t)b * n_kv + kvh) * d + dim) * tcap + pos] = __ldcg(vsrc + i);
+    }
+  }
+}
+void launch_rope_append(bf16* qkv, int batch, int qkv_cols, int n_head, int n_kv, int d, const bf16* cos_t,
+                        const bf16* sin_t, bf16* kcache, bf16* vtcache, const GenState* state, int tcap, int max_pos,
+                        bool pdl, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(batch); cfg.blockDim = dim3(256); cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, rope_append_kernel, qkv, qkv_cols, n_head, n_kv, d, cos_t, sin_t, kcache, vtcache, state, tcap,
+                     max_pos);
+  count_launch();
+}
+
 void launch_rope(bf16* qkv, int rows, int seq, int qkv_cols, int n_rot_heads, int d, const bf16* cos_t, const bf16* sin_t,
                  const GenState* state, int max_pos, cudaStream_t st) {
   rope_kernel<<<rows, 256, 0, st>>>(qkv, seq, qkv_cols, n_rot_heads, d, cos_t, sin_t, state, max_pos);
