@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstarvector_b200.so")
+LIB_PATH = os.environ.get("SV_LIB_PATH") or os.path.join(_HERE, "libstarvector_b200.so")   # SV_LIB_PATH: A/B builds
 
 SV_OK, SV_ERR_INVALID, SV_ERR_CUDA, SV_ERR_UNSUPPORTED, SV_ERR_STATE = 0, -1, -2, -3, -4
 SV_DTYPE_BF16, SV_DTYPE_F32, SV_DTYPE_F16 = 0, 1, 2

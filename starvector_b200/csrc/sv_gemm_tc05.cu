@@ -16,6 +16,7 @@
 // Every mbarrier wait is bounded: a protocol bug traps (CUDA error) instead of hanging the GPU.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -32,7 +33,12 @@ constexpr int kThreads = 192;
 
 template <int BN> struct Cfg {
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
-  static constexpr int kStages = (BN == 128) ? 6 : 8;
+#ifndef SV_TC05_STAGES64
+#define SV_TC05_STAGES64 4
+#define SV_TC05_STAGES128 3
+#define SV_TC05_MINCTAS 2
+#endif
+  static constexpr int kStages = (BN == 128) ? SV_TC05_STAGES128 : SV_TC05_STAGES64;   // ~96 KB per CTA: CTAs share an SM
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual 1 KiB alignment
   static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;                      // power of two >= 32
@@ -108,7 +114,7 @@ SV_DEVINL void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) linear_tc05_kernel(const __grid_constant__ CUtensorMap tmap_x,
+__global__ void __launch_bounds__(kThreads, SV_TC05_MINCTAS) linear_tc05_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                                   const __grid_constant__ CUtensorMap tmap_w,
                                                                   const bf16* __restrict__ bias,
                                                                   const bf16* __restrict__ res, bf16* __restrict__ Y,
@@ -299,7 +305,9 @@ cudaError_t launch_linear_tc05(const bf16* x, const bf16* w, const bf16* bias, c
   const int mt = (M + tc05::BM - 1) / tc05::BM;
   static int nsm = 0;
   if (nsm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); if (nsm <= 0) nsm = 148; }
-  const bool wide = (N % 128 == 0) && ((int64_t)mt * ((N + 63) / 64) > nsm);
+  static int per_sm = 0;                       // CTAs of this kernel that fit one SM (2 with the 96 KB ring)
+  if (per_sm == 0) { const char* c = getenv("SV_TC05_PER_SM"); per_sm = c ? atoi(c) : 2; if (per_sm < 1) per_sm = 1; }
+  const bool wide = (N % 128 == 0) && ((int64_t)mt * ((N + 63) / 64) > (int64_t)nsm * per_sm);
   return wide ? tc05::launch<128>(x, w, bias, res, y, M, N, K, act, st)
               : tc05::launch<64>(x, w, bias, res, y, M, N, K, act, st);
 }
