@@ -137,6 +137,9 @@ SV_API int sv_prefill_embeds(sv_engine* e, const void* inputs_embeds, int32_t ba
 /* One teacher-forced decode step: feed ids int32 [B], append to the KV cache, return fp32 logits
  * [B,V] (optional).  The parity-test hook; also the body the generate loop replays. */
 SV_API int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream);
+/* Beam search support: permute the image rows of the KV cache, row r <- row src_rows[r]
+ * (int32 [B] on the device) for the tokens cached so far = HF `_reorder_cache` (vendored modeling_gpt_bigcode.py:1282-1291). */
+SV_API int sv_reorder_cache(sv_engine* e, const int32_t* src_rows, void* stream);
 /* GenerationMixin.generate() after the prefill (greedy / sampling loop, App. B): runs up to
  * max_new_tokens steps as a replayed CUDA graph.  out_ids int32 [B,max_new_tokens] (new tokens
  * only, padded with pad_token_id), out_len int32 [B] = rectangular generated length.

@@ -80,6 +80,7 @@ struct sv_engine {
   unsigned int* mega_barrier = nullptr;
   long long* mega_dbg = nullptr;
   bool mega_debug = false;
+  bf16 *kscratch = nullptr, *vscratch = nullptr;   // one layer of cache, for beam-search reorders
   bf16 *kcache, *vtcache;           // [layer][max_batch][n_kv][tcap][D] / [layer][max_batch][n_kv][D][tcap]
   int64_t cache_layer_stride = 0;
   GenState* state = nullptr;
@@ -312,6 +313,7 @@ bool build_buffers(sv_engine* e) {
   AL(mega_layers, d.n_layer); AL(mega_barrier, 4); AL(mega_dbg, 1024);
   e->cache_layer_stride = B * d.n_kv_head * (int64_t)e->tcap * D;
   AL(kcache, e->cache_layer_stride * d.n_layer); AL(vtcache, e->cache_layer_stride * d.n_layer);
+  AL(kscratch, e->cache_layer_stride); AL(vscratch, e->cache_layer_stride);
   AL(state, 1); AL(params, 1); AL(seen, B * d.vocab); AL(next_ids, B); AL(out_ids, B * (int64_t)d.max_len);
   AL(ids_tmp, B * kMaxPrompt);
 #undef AL
@@ -987,6 +989,24 @@ int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_t batch
   cudaFree(px);
   cudaFree(dout);
   return r;
+}
+
+int sv_reorder_cache(sv_engine* e, const int32_t* src_rows, void* stream) {
+  if (!e || !src_rows) return fail(e, SV_ERR_INVALID, "null argument");
+  if (!e->prefilled) return fail(e, SV_ERR_STATE, "sv_reorder_cache needs a prefilled cache");
+  SV_CK(e, cudaSetDevice(e->device));
+  LaunchScope scope(e);
+  cudaStream_t st = (cudaStream_t)stream;
+  const sv_model_desc& d = e->d;
+  const int B = e->cur_batch, len = e->host_cur_len;
+  for (int i = 0; i < d.n_layer; ++i) {
+    bf16* kc = e->kcache + e->cache_layer_stride * i;
+    bf16* vc = e->vtcache + e->cache_layer_stride * i;
+    launch_kv_gather(kc, vc, e->kscratch, e->vscratch, src_rows, B, d.n_kv_head, e->tcap, d.head_dim, len, st);
+    launch_kv_gather(e->kscratch, e->vscratch, kc, vc, nullptr, B, d.n_kv_head, e->tcap, d.head_dim, len, st);
+  }
+  SV_CK(e, cudaGetLastError());
+  return SV_OK;
 }
 
 int64_t sv_launch_count(const sv_engine* e) { return e ? e->launches : 0; }

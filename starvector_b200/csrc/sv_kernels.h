@@ -48,6 +48,8 @@ void launch_kv_scatter(const bf16* qkv, bf16* kcache, bf16* vtcache, int batch, 
                        int tcap, int max_batch_unused, cudaStream_t st);
 void launch_kv_append(const bf16* qkv, bf16* kcache, bf16* vtcache, const GenState* state, int batch, int q_cols,
                       int n_kv, int d, int tcap, cudaStream_t st);
+void launch_kv_gather(const bf16* ksrc, const bf16* vsrc, bf16* kdst, bf16* vdst, const int32_t* idx, int rows, int n_kv,
+                      int tcap, int d, int len, cudaStream_t st);
 void launch_gather_rows(const bf16* x, bf16* y, int batch, int seq, int row, int h, cudaStream_t st);
 void launch_logits_to_float(const bf16* logits, float* out, int64_t n, cudaStream_t st);
 void launch_select_greedy(const bf16* logits, int vocab, int batch, GenState* state, const GenParamsDev* params,

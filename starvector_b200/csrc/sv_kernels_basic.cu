@@ -321,6 +321,35 @@ void launch_kv_append(const bf16* qkv, bf16* kcache, bf16* vtcache, const GenSta
   count_launch();
 }
 
+// Beam search cache reorder (HF `_reorder_cache` / `Cache.reorder_cache`, generation/utils.py beam loop): image row r of
+// the destination takes the first `len` tokens of source row idx[r].  One layer at a time through a scratch layer
+// (gather), then copied back with idx == nullptr (identity).  grid = (n_kv * 2, rows); 16-byte vectors.
+__global__ void kv_gather_kernel(const bf16* __restrict__ ksrc, const bf16* __restrict__ vsrc, bf16* __restrict__ kdst,
+                                 bf16* __restrict__ vdst, const int32_t* __restrict__ idx, int n_kv, int tcap, int d,
+                                 int len) {
+  const int r = blockIdx.y, kvh = blockIdx.x >> 1, which = blockIdx.x & 1;
+  const int sr = idx ? idx[r] : r;
+  if (which == 0) {            // K rows: contiguous [len][d]
+    const uint4* s = reinterpret_cast<const uint4*>(ksrc + ((int64_t)sr * n_kv + kvh) * tcap * d);
+    uint4* t = reinterpret_cast<uint4*>(kdst + ((int64_t)r * n_kv + kvh) * tcap * d);
+    const int n = len * d / 8;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t[i] = s[i];
+  } else {                     // V^T: d rows of `len` (rounded up to 8) keys
+    const int per = (len + 7) / 8;
+    for (int i = threadIdx.x; i < d * per; i += blockDim.x) {
+      const int dim = i / per, c = i % per;
+      const int64_t off = (((int64_t)0 * n_kv + kvh) * d + dim) * tcap + c * 8;
+      *reinterpret_cast<uint4*>(vdst + ((int64_t)r * n_kv * d) * tcap + off) =
+          *reinterpret_cast<const uint4*>(vsrc + ((int64_t)sr * n_kv * d) * tcap + off);
+    }
+  }
+}
+void launch_kv_gather(const bf16* ksrc, const bf16* vsrc, bf16* kdst, bf16* vdst, const int32_t* idx, int rows, int n_kv,
+                      int tcap, int d, int len, cudaStream_t st) {
+  kv_gather_kernel<<<dim3(n_kv * 2, rows), 256, 0, st>>>(ksrc, vsrc, kdst, vdst, idx, n_kv, tcap, d, len);
+  count_launch();
+}
+
 __global__ void gather_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int seq, int row, int h) {
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < h; c += blockDim.x) y[(int64_t)b * h + c] = x[((int64_t)b * seq + row) * h + c];

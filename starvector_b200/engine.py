@@ -198,6 +198,14 @@ class Engine:
                                               _stream_ptr(self.device)))
         return logits
 
+    def reorder_cache(self, src_rows: torch.Tensor) -> None:
+        """KV-cache row permutation for beam search: row r <- row src_rows[r]."""
+        idx = self._dev(src_rows, torch.int32).reshape(-1)
+        if idx.numel() != self._batch:
+            raise ValueError("src_rows must have one entry per cache row")
+        with self._lock:
+            self._ck(self._lib.sv_reorder_cache(self._h, C.c_void_p(idx.data_ptr()), _stream_ptr(self.device)))
+
     def generate(self, params: GenerationParams) -> torch.Tensor:
         """Run the decode loop after a prefill. Returns int32 [B, n_generated] (new tokens only)."""
         B, n = self._batch, int(params.max_new_tokens)

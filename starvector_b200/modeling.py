@@ -42,6 +42,9 @@ class _Transformer:
             raise NotImplementedError("padded prefixes never occur on the im2svg path and are not built")
         o = self._o
         params = o._gen_params(kw, prefix_len=inputs_embeds.shape[1])
+        nb = int(kw.get("num_beams", 1))
+        if nb > 1:
+            return o._beam_generate(params, kw, nb, inputs_embeds=inputs_embeds)
         o.engine.prefill_embeds(inputs_embeds)
         return o.engine.generate(params).long()
 
@@ -139,11 +142,6 @@ class StarVectorStarCoder:
     def _gen_params(self, kw: Dict[str, Any], prefix_len: int) -> GenerationParams:
         """`_get_generation_kwargs` (:223-241) + `_get_im2svg_specific_kwargs` (:289-295) + HF length fix-up."""
         do_sample = bool(kw.get("use_nucleus_sampling", kw.get("do_sample", True)))
-        num_beams = int(kw.get("num_beams", 2))
-        if num_beams != 1:
-            warnings.warn(
-                f"num_beams={num_beams}: beam search / beam-sample is not built yet (SURVEY.md §8f-1); decoding with "
-                "num_beams=1. Pass num_beams=1 to silence this.", RuntimeWarning, stacklevel=3)
         max_length = int(kw.get("max_length", 30))
         max_new = kw.get("max_new_tokens")
         if max_new is None:
@@ -164,6 +162,19 @@ class StarVectorStarCoder:
             seed=int(kw.get("seed", self.seed)),
         )
 
+    def _beam_generate(self, params: GenerationParams, kw: Dict[str, Any], num_beams: int, image=None, prompt_ids=None,
+                       inputs_embeds=None) -> torch.Tensor:
+        """num_beams > 1 (the reference default is 2, starvector_base.py:234): beam search / beam-sample with
+        `early_stopping=True` (:292) and the caller's `length_penalty` — bookkeeping in beam_search.py."""
+        from .beam_search import beam_search
+
+        return beam_search(
+            self.engine, image, prompt_ids, inputs_embeds=inputs_embeds, num_beams=num_beams,
+            max_new_tokens=params.max_new_tokens, do_sample=params.do_sample, temperature=params.temperature,
+            top_p=params.top_p, repetition_penalty=params.repetition_penalty,
+            length_penalty=float(kw.get("length_penalty", 1.0)), early_stopping=True,
+            eos_token_id=params.eos_token_id, pad_token_id=params.pad_token_id, stop_ids=params.stop_ids, seed=params.seed)
+
     # -- the path ------------------------------------------------------------------------
     @torch.no_grad()
     def generate_im2svg_ids(self, batch: Dict[str, torch.Tensor], **kwargs) -> torch.Tensor:
@@ -171,6 +182,10 @@ class StarVectorStarCoder:
         image = batch["image"]
         prompt_ids = self._tokenize_prompt(kwargs.get("prompt"), image.shape[0])
         params = self._gen_params(kwargs, prefix_len=self.query_length + prompt_ids.shape[1])
+        num_beams = int(kwargs.get("num_beams", 2))                             # reference default (:234)
+        if num_beams > 1:
+            out = self._beam_generate(params, kwargs, num_beams, image=image, prompt_ids=prompt_ids)
+            return torch.cat([prompt_ids.to(out.device), out.long()], dim=1)
         self.engine.encode_images(image)
         self.engine.prefill(prompt_ids)
         out = self.engine.generate(params)
