@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SV_ABI_VERSION 2
+#define SV_ABI_VERSION 3
 #if defined(__GNUC__)
 #define SV_API __attribute__((visibility("default")))
 #else
@@ -174,6 +174,53 @@ SV_API int sv_op_linear(int32_t impl, const void* x, const void* w, const void* 
 SV_API int sv_op_attention_vit(const void* qkv, void* out, int32_t batch, int32_t seq, int32_t heads, void* stream);
 /* Causal multi-query attention over packed qkv [B*T, heads*D + 2*D] (D=128) -> out [B*T, heads*D]. */
 SV_API int sv_op_attention_mqa(const void* qkv, void* out, int32_t batch, int32_t seq, int32_t heads, void* stream);
+
+/* ---- image preprocessing ------------------------------------------------ */
+/* Replaces `ImageTrainProcessor.__call__` (reference starvector/data/util.py:40-66: RGBA pasted on white, pad to
+ * square with 255, `transforms.Resize(size, BICUBIC)` on the PIL image, ToTensor, Normalize) and
+ * `SimpleStarVectorProcessor.transform` (starvector_arch.py:39-45: the same with `convert("RGB")` for RGBA),
+ * bit for bit with Pillow's 8-bit resample.  On-wire input = what PIL holds: uint8 HWC host buffers. */
+enum { SV_ALPHA_WHITE = 0 /* data/util.py:63-66 */, SV_ALPHA_DROP = 1 /* starvector_arch.py:40 */ };
+
+typedef struct sv_preproc sv_preproc;
+
+typedef struct sv_preproc_desc {
+  int32_t out_size;    /* S: output is [n,3,S,S] (224 for CLIP ViT-L/14, data/util.py:41) */
+  int32_t alpha_mode;  /* SV_ALPHA_WHITE | SV_ALPHA_DROP: what happens to a 4th channel */
+  int32_t pad_square;  /* 1: pad the shorter side with 255 to a centred square first (data/util.py:55-61); 0: resize (w,h)->(S,S) */
+  int32_t out_dtype;   /* SV_DTYPE_BF16 (what sv_encode_images takes) | SV_DTYPE_F32 (the reference's tensor, for parity) */
+  float mean[3];       /* Normalize(mean, std), data/util.py:33-38 */
+  float std[3];
+} sv_preproc_desc;
+
+typedef struct sv_image_u8 {
+  const uint8_t* data; /* HOST pointer, uint8 [height][width][channels]; pinned memory makes the upload asynchronous */
+  int32_t width, height;
+  int32_t channels;    /* 3 (RGB) or 4 (RGBA) */
+  int32_t row_stride;  /* bytes between rows; 0 = width*channels */
+} sv_image_u8;
+
+SV_API int sv_preproc_create(const sv_preproc_desc* desc, int device, sv_preproc** out);
+SV_API void sv_preproc_destroy(sv_preproc* p);
+/* Message for the last failing call on `p` (or the last failing create when p == NULL). */
+SV_API const char* sv_preproc_last_error(const sv_preproc* p);
+/* `[processor(img) for img in images]` + stack: uploads the n images (ragged sizes), runs the horizontal and the
+ * vertical resample pass, writes DEVICE out_pixels [n,3,S,S] (out_dtype).  Asynchronous on `stream`. */
+SV_API int sv_preproc_run_host(sv_preproc* p, const sv_image_u8* images_host, int32_t n, void* out_pixels, void* stream);
+/* Kernels launched by `p` so far. */
+SV_API long long sv_preproc_launch_count(const sv_preproc* p);
+/* Host-only pieces of the above, exported so that they can be checked against Pillow / torch without a GPU:
+ * the fixed-point resample taps of one axis (Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc; call with
+ * bounds == taps == NULL to query ksize; bounds int32 [out_size][2] = first tap, tap count; taps int32
+ * [out_size][ksize]) and the 3x256 ToTensor+Normalize table (float [3][256]). */
+SV_API int sv_resample_coeffs_host(int32_t in_size, int32_t out_size, int32_t* ksize, int32_t* bounds, int32_t* taps,
+                                   int32_t taps_capacity);
+SV_API int sv_preproc_lut_host(const sv_preproc_desc* desc, float* lut768);
+/* The batch plan sv_preproc_run_host uploads: per-image metadata (padding, arena offsets) followed by the coefficient
+ * arena.  sizes[5] = {blob bytes, metadata bytes, input-arena bytes, intermediate pixels, max input rows}; blob may be
+ * NULL to query sizes.  Test hook: tests/test_preprocess_emul.py replays the kernels' index arithmetic from it. */
+SV_API int sv_preproc_plan_host(const sv_preproc_desc* desc, const sv_image_u8* images_host, int32_t n, void* blob,
+                                int64_t blob_capacity, int64_t sizes[5]);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,8 @@ SV_OK, SV_ERR_INVALID, SV_ERR_CUDA, SV_ERR_UNSUPPORTED, SV_ERR_STATE = 0, -1, -2
 SV_DTYPE_BF16, SV_DTYPE_F32, SV_DTYPE_F16 = 0, 1, 2
 SV_ACT_NONE, SV_ACT_QUICKGELU, SV_ACT_GELU_TANH, SV_ACT_SILU = 0, 1, 2, 3
 SV_LINEAR_AUTO, SV_LINEAR_ROWGROUP, SV_LINEAR_TCGEN05 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
+SV_ALPHA_WHITE, SV_ALPHA_DROP = 0, 1
 
 
 class ModelDesc(C.Structure):
@@ -34,6 +35,16 @@ class GenParams(C.Structure):
         ("n_stop_ids", C.c_int32), ("stop_ids", C.c_int32 * 8), ("stop_row0_only", C.c_int32),
         ("seed", C.c_uint64), ("poll_interval", C.c_int32),
     ]
+
+
+class PreprocDesc(C.Structure):
+    _fields_ = [("out_size", C.c_int32), ("alpha_mode", C.c_int32), ("pad_square", C.c_int32), ("out_dtype", C.c_int32),
+                ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+
+
+class ImageU8(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
+                ("row_stride", C.c_int32)]
 
 
 # name -> (restype, argtypes); must list every SV_API symbol of the header (tests check this)
@@ -60,6 +71,14 @@ SIGNATURES = {
     "sv_op_linear": (C.c_int, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "sv_op_attention_vit": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "sv_op_attention_mqa": (C.c_int, [_P, _P, _I, _I, _I, _P]),
+    "sv_preproc_create": (C.c_int, [C.POINTER(PreprocDesc), C.c_int, C.POINTER(_P)]),
+    "sv_preproc_destroy": (None, [_P]),
+    "sv_preproc_last_error": (C.c_char_p, [_P]),
+    "sv_preproc_run_host": (C.c_int, [_P, C.POINTER(ImageU8), _I, _P, _P]),
+    "sv_preproc_launch_count": (C.c_longlong, [_P]),
+    "sv_resample_coeffs_host": (C.c_int, [_I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _I]),
+    "sv_preproc_lut_host": (C.c_int, [C.POINTER(PreprocDesc), C.POINTER(C.c_float)]),
+    "sv_preproc_plan_host": (C.c_int, [C.POINTER(PreprocDesc), C.POINTER(ImageU8), _I, _P, C.c_int64, C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -20,6 +20,7 @@ import torch
 
 from .config import ModelDims, StarVectorConfig
 from .engine import Engine, GenerationParams
+from .preprocess import ImageTrainProcessor, SiglipImageProcessor
 from .tokenizer import load_tokenizer
 from .weights import DEC, DEC2, synthetic_state_dict
 
@@ -65,41 +66,14 @@ class _ImageEncoder:
     def __init__(self, owner: "StarVectorStarCoder"):
         self._o = owner
 
-    def process_images(self, images) -> List[torch.Tensor]:
-        return [self._o.processor(im).unsqueeze(0) for im in images]
+    def process_images(self, images):
+        if self._o.v2:                                                          # image_encoder.py:119
+            return self._o.processor(images=images, return_tensors="pt").pixel_values.unsqueeze(0)
+        return [x.unsqueeze(0) for x in self._o.processor.batch(images)]        # image_encoder.py:113-117, one upload + 2 launches
 
     def __call__(self, image: torch.Tensor) -> torch.Tensor:
         _, vit = self._o.engine.encode_images(image, return_vit=True)
         return vit
-
-
-class ImageTrainProcessor:
-    """RGBA->white, pad to square (white), bicubic resize, ToTensor, CLIP normalise (data/util.py:40-66)."""
-
-    def __init__(self, size: int = 224):
-        self.size = size
-
-    def __call__(self, img) -> torch.Tensor:
-        from PIL import Image
-        import numpy as np
-
-        if img.mode == "RGBA":
-            bg = Image.new("RGB", img.size, (255, 255, 255))
-            bg.paste(img, mask=img.split()[3])
-            img = bg
-        img = img.convert("RGB")
-        w, h = img.size
-        m = max(w, h)
-        if w != h:
-            sq = Image.new("RGB", (m, m), (255, 255, 255))
-            sq.paste(img, ((m - w) // 2, (m - h) // 2))
-            img = sq
-        if img.size != (self.size, self.size):
-            img = img.resize((self.size, self.size), Image.BICUBIC)
-        x = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255.0)
-        mean = torch.tensor(CLIP_MEAN).view(3, 1, 1)
-        std = torch.tensor(CLIP_STD).view(3, 1, 1)
-        return (x - mean) / std
 
 
 class StarVectorStarCoder:
@@ -114,7 +88,10 @@ class StarVectorStarCoder:
         self.max_length = config.max_length_train - self.query_length - 4      # starvector_base.py:41
         self.llm_config = {"hidden_size": engine.dims.hidden, "vocab_size": engine.dims.vocab,
                            "n_positions": engine.dims.n_positions}
-        self.processor = ImageTrainProcessor(size=engine.dims.image_size)
+        # image_encoder.py:25 (clip: ImageTrainProcessor) / :32-48 (siglip: the hub's SiglipProcessor); both run on the GPU
+        dev_index = engine.device.index or 0
+        self.processor = (SiglipImageProcessor(size=engine.dims.image_size, device=dev_index) if v2
+                          else ImageTrainProcessor(size=engine.dims.image_size, device=dev_index))
         self.svg_transformer = _SvgTransformer(self, tokenizer)
         self.image_encoder = _ImageEncoder(self)
         self.image_projection = self._project

@@ -32,6 +32,22 @@ def test_quickstart_shaped_call(model):
     assert isinstance(out, list) and len(out) == 1 and out[0].startswith("<svg")
 
 
+def test_process_images_then_generate_like_quickstart(model):
+    """quickstart.py:15-19: `process_images([pil])[0].to(float16).cuda()` -> generate_im2svg; pixels == the reference recipe."""
+    from PIL import Image
+
+    from oracle import preprocess as P
+
+    d, sd, m = model
+    arr = P.synthetic_image(90, 61, 4, seed=3)
+    pix = m.process_images([Image.fromarray(arr, "RGBA")])
+    assert isinstance(pix, list) and pix[0].shape == (1, 3, d.image_size, d.image_size) and pix[0].is_cuda
+    assert torch.equal(pix[0][0].cpu(), P.reference_transform(arr, d.image_size, P.ALPHA_WHITE))
+    image = pix[0].to(torch.float16).cuda()
+    out = m.generate_im2svg({"image": image}, use_nucleus_sampling=False, num_beams=1, max_length=d.query_length + 2 + 8)
+    assert len(out) == 1 and out[0].startswith("<svg")
+
+
 def test_greedy_strings_match_oracle(model):
     d, sd, m = model
     img = synthetic_images(d, 2, seed=1)
