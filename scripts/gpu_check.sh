@@ -13,6 +13,7 @@ SV_PDL=0 run engine_graph_nopdl python -m pytest tests/test_engine_gpu.py -q --t
 SV_DECODE=legacy run engine_legacy python -m pytest tests/test_engine_gpu.py -q --tb=short -m gpu
 run v2 python -m pytest tests/test_v2_gpu.py -q --tb=short -m gpu
 SV_DECODE=fused run v2_fused python -m pytest tests/test_v2_gpu.py -q --tb=short -m gpu
+run preprocess python -m pytest tests/test_preprocess_gpu.py -q --tb=short -m gpu
 run beam python -m pytest tests/test_beam_gpu.py -q --tb=short -m gpu
 run full_1b python -m pytest tests/test_full_1b_gpu.py -q --tb=short -m gpu
 run smoke python __graft_entry__.py --smoke

@@ -173,13 +173,26 @@ class StarVectorStarCoder:
         return self.svg_transformer.tokenizer.batch_decode(ids, skip_special_tokens=True)          # :257
 
     def generate_im2svg_grpo(self, batch, **kwargs):                                               # :261-286
-        if kwargs.get("num_return_sequences", 1) != 1:
-            raise NotImplementedError("num_return_sequences > 1 is not built (SURVEY.md §8f-4)")
-        kwargs.setdefault("num_beams", 1)
-        ids = self.generate_im2svg_ids(batch, **kwargs)
-        emb, _ = self.engine.encode_images(batch["image"], return_embeds=True)
+        """`num_return_sequences` completions per image (sampled independently, `num_beams` forced to 1, :277-280):
+        HF's `_expand_inputs_for_generation` = every image row repeated G times, adjacent.  Returns the reference's dict;
+        `outputs` is `[B*G, P + n_new]`, `inputs_embeds` the un-expanded `[B, Q+P, H]` prefix embeddings."""
+        G = int(kwargs.get("num_return_sequences", 1))
+        if G < 1:
+            raise ValueError("num_return_sequences must be >= 1")
+        image = batch["image"]
+        if G > 1:
+            if image.shape[0] * G > self.engine.dims.max_batch:
+                raise ValueError(f"batch {image.shape[0]} x num_return_sequences {G} exceeds the engine's max_batch "
+                                 f"{self.engine.dims.max_batch}")
+            kwargs = dict(kwargs, num_beams=1)
+        else:
+            kwargs.setdefault("num_beams", 1)
+        ids = self.generate_im2svg_ids({"image": image.repeat_interleave(G, dim=0) if G > 1 else image}, **kwargs)
+        emb, _ = self.engine.encode_images(image, return_embeds=True)
+        prompt_ids = self._tokenize_prompt(kwargs.get("prompt"), image.shape[0])
+        inputs_embeds = torch.cat([emb, self._get_embeddings(prompt_ids.to(emb.device))], dim=1)    # :217-219
         return {"raw_svg": self.svg_transformer.tokenizer.batch_decode(ids, skip_special_tokens=True),
-                "outputs": ids, "inputs_embeds": emb}
+                "outputs": ids, "inputs_embeds": inputs_embeds}
 
 
 class StarVectorForCausalLM:

@@ -78,3 +78,22 @@ def test_max_length_shorter_than_prefix_raises(model):
     d, sd, m = model
     with pytest.raises(ValueError, match="max_length"):
         m.generate_im2svg({"image": synthetic_images(d, 1)}, num_beams=1, max_length=d.query_length)   # < Q + P
+
+
+def test_grpo_num_return_sequences(model):
+    """starvector_base.py:261-286: G completions per image = rows repeated adjacently, sampled independently."""
+    d, sd, m = model
+    img = synthetic_images(d, 2, seed=1).cuda()
+    P = len(m.model.svg_transformer.tokenizer("<svg")["input_ids"])
+    kw = dict(max_length=d.query_length + P + 10)
+    two = m.model.generate_im2svg_grpo({"image": img}, use_nucleus_sampling=False, num_return_sequences=2, **kw)
+    assert two["outputs"].shape[0] == 4 and len(two["raw_svg"]) == 4
+    assert torch.equal(two["outputs"][0], two["outputs"][1]) and torch.equal(two["outputs"][2], two["outputs"][3])
+    one = m.model.generate_im2svg_grpo({"image": img}, use_nucleus_sampling=False, **kw)
+    assert torch.equal(one["outputs"], two["outputs"][::2])
+    assert two["inputs_embeds"].shape == (2, d.query_length + P, d.hidden)
+    s = m.model.generate_im2svg_grpo({"image": img[:1]}, num_return_sequences=4, temperature=2.0, top_p=1.0, **kw)
+    assert s["outputs"].shape[0] == 4
+    assert len({tuple(r.tolist()) for r in s["outputs"]}) >= 3          # independent samples per copy
+    with pytest.raises(ValueError):
+        m.model.generate_im2svg_grpo({"image": img}, num_return_sequences=3, **kw)      # 6 rows > max_batch 4
