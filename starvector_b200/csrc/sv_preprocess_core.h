@@ -42,15 +42,19 @@ SV_HD uint32_t fetch_rgb(const uint8_t* __restrict__ arena, const ImageMeta& im,
   const int sy = y - im.pad_top, sx = x - im.pad_left;
   if (sy < 0 || sy >= im.height || sx < 0 || sx >= im.width) return 0x00FFFFFFu;
   const uint8_t* p = arena + im.src_off + (int64_t)sy * im.row_stride + (int64_t)sx * im.channels;
-  int r = p[0], g = p[1], b = p[2];
-  if (im.channels == 4 && im.alpha_white) {
-    const int m = p[3];
+  if (im.channels == 4) {
+    // one 32-bit load per RGBA pixel: the arena base is cudaMalloc-aligned, src_off a multiple of 16 and rows are tight
+    // (row_stride = 4*width), so every pixel is 4-byte aligned; bytes are little-endian r,g,b,a
+    const uint32_t px = *reinterpret_cast<const uint32_t*>(p);
+    if (!im.alpha_white) return px & 0x00FFFFFFu;
+    const int m = (int)(px >> 24);
     const int keep = muldiv255(255, 255 - m);
-    r = keep + muldiv255(r, m);
-    g = keep + muldiv255(g, m);
-    b = keep + muldiv255(b, m);
+    const int r = keep + muldiv255((int)(px & 255u), m);
+    const int g = keep + muldiv255((int)((px >> 8) & 255u), m);
+    const int b = keep + muldiv255((int)((px >> 16) & 255u), m);
+    return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
   }
-  return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
 }
 
 SV_HD int clip8(int acc) {
