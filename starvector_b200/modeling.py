@@ -11,6 +11,7 @@ failures), as the reference's callers expect (serve/model_worker.py:183-207).
 """
 from __future__ import annotations
 
+import dataclasses
 import json
 import os
 import warnings
@@ -20,6 +21,7 @@ import torch
 
 from .config import ModelDims, StarVectorConfig
 from .engine import Engine, GenerationParams
+from .parallel import merge_generated
 from .preprocess import ImageTrainProcessor, SiglipImageProcessor
 from .tokenizer import load_tokenizer
 from .weights import DEC, DEC2, synthetic_state_dict
@@ -163,9 +165,22 @@ class StarVectorStarCoder:
         if num_beams > 1:
             out = self._beam_generate(params, kwargs, num_beams, image=image, prompt_ids=prompt_ids)
             return torch.cat([prompt_ids.to(out.device), out.long()], dim=1)
-        self.engine.encode_images(image)
-        self.engine.prefill(prompt_ids)
-        out = self.engine.generate(params)
+        mb = self.engine.dims.max_batch
+        if image.shape[0] <= mb:
+            self.engine.encode_images(image)
+            self.engine.prefill(prompt_ids)
+            out = self.engine.generate(params)
+        else:
+            # More images than the engine holds at once: run max_batch-sized groups one after another and rebuild the
+            # single-call rectangle with the rule the multi-GPU path uses (parallel.merge_generated): only the group that
+            # contains global row 0 arms the row-0 `</svg>` stop, rows are independent, so prefixes are identical.
+            groups = []
+            for lo in range(0, image.shape[0], mb):
+                p = params if lo == 0 else dataclasses.replace(params, stop_ids=(), seed=params.seed + lo)
+                self.engine.encode_images(image[lo:lo + mb])
+                self.engine.prefill(prompt_ids[lo:lo + mb])
+                groups.append(self.engine.generate(p))
+            out = merge_generated(groups, params.stop_ids, params.pad_token_id)
         return torch.cat([prompt_ids.to(out.device), out.long()], dim=1)
 
     def generate_im2svg(self, batch: Dict[str, torch.Tensor], **kwargs) -> List[str]:

@@ -97,3 +97,20 @@ def test_grpo_num_return_sequences(model):
     assert len({tuple(r.tolist()) for r in s["outputs"]}) >= 3          # independent samples per copy
     with pytest.raises(ValueError):
         m.model.generate_im2svg_grpo({"image": img}, num_return_sequences=3, **kw)      # 6 rows > max_batch 4
+
+
+def test_more_images_than_max_batch_runs_in_groups(model):
+    """6 images on an engine that holds 4: two groups, merged with the row-0 stop rule of the sharded path."""
+    from starvector_b200.parallel import merge_generated
+
+    d, sd, m = model
+    img = synthetic_images(d, 6, seed=4).cuda()
+    tok = m.model.svg_transformer.tokenizer
+    P = len(tok("<svg")["input_ids"])
+    kw = dict(use_nucleus_sampling=False, num_beams=1, max_length=d.query_length + P + 12)
+    all6 = m.model.generate_im2svg_ids({"image": img}, **kw)
+    first = m.model.generate_im2svg_ids({"image": img[:4]}, **kw)[:, P:]
+    rest = m.model.generate_im2svg_ids({"image": img[4:]}, stop_ids=(), **kw)[:, P:]
+    want = merge_generated([first, rest], tok("</svg>")["input_ids"], tok.pad_token_id)
+    assert all6.shape[0] == 6 and torch.equal(all6[:, P:], want)
+    assert len(m.model.generate_im2svg({"image": img}, **kw)) == 6
