@@ -145,6 +145,14 @@ SV_API int sv_reorder_cache(sv_engine* e, const int32_t* src_rows, void* stream)
  * only, padded with pad_token_id), out_len int32 [B] = rectangular generated length.
  * Synchronises `stream` before returning. */
 SV_API int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t* out_len, void* stream);
+/* sv_generate with token streaming (serve/model_worker.py:161-181 hands a `streamer` to generate(),
+ * which the reference's kwarg whitelist drops, starvector_base.py:223-241).  Every `poll_interval` steps, and once at the
+ * end, `on_tokens(user, ids_host, batch, first_step, n_steps)` is called on the calling thread with the new tokens of
+ * every row, ids_host int32 [batch][n_steps] (valid during the call); the concatenation over calls is exactly the
+ * rectangle sv_generate returns.  A non-zero return cancels the generation after the current poll. */
+typedef int (*sv_token_callback)(void* user, const int32_t* ids_host, int32_t batch, int32_t first_step, int32_t n_steps);
+SV_API int sv_generate_stream(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t* out_len,
+                              sv_token_callback on_tokens, void* user, void* stream);
 /* Whole path with HOST buffers (copies inside): pixels_host bf16 [B,3,S,S], prompt_ids_host
  * int32 [B,P] -> out_ids_host int32 [B,max_new_tokens], out_len_host int32 [B]. */
 SV_API int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_t batch,

@@ -47,6 +47,8 @@ class ImageU8(C.Structure):
                 ("row_stride", C.c_int32)]
 
 
+TOKEN_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32)   # sv_token_callback
+
 # name -> (restype, argtypes); must list every SV_API symbol of the header (tests check this)
 _P, _I, _F = C.c_void_p, C.c_int32, C.c_float
 SIGNATURES = {
@@ -62,6 +64,7 @@ SIGNATURES = {
     "sv_decode_step": (C.c_int, [_P, _P, _P, _P]),
     "sv_reorder_cache": (C.c_int, [_P, _P, _P]),
     "sv_generate": (C.c_int, [_P, C.POINTER(GenParams), _P, _P, _P]),
+    "sv_generate_stream": (C.c_int, [_P, C.POINTER(GenParams), _P, _P, TOKEN_CALLBACK, _P, _P]),
     "sv_generate_im2svg_host": (C.c_int, [_P, _P, _I, _P, _I, C.POINTER(GenParams), _P, _P, _P]),
     "sv_launch_count": (C.c_int64, [_P]),
     "sv_engine_describe": (C.c_char_p, [_P]),

@@ -25,6 +25,7 @@ using namespace sv;
 namespace {
 
 constexpr int kMaxPrompt = 64;
+constexpr int kStreamChunk = 1024;   // tokens per row handed to a streaming callback at once
 constexpr int kMaxSplit = 128;
 
 std::string g_create_error;
@@ -88,6 +89,7 @@ struct sv_engine {
   uint8_t* seen = nullptr;
   int32_t *next_ids = nullptr, *out_ids = nullptr, *ids_tmp = nullptr;
   int32_t* host_flag = nullptr;     // pinned
+  int32_t* host_stream = nullptr;   // pinned staging of streamed tokens [max_batch][kStreamChunk], allocated on first use
 
   // run state (host mirror)
   int cur_batch = 0, prefix_len = 0, host_cur_len = 0;
@@ -684,6 +686,7 @@ void sv_engine_destroy(sv_engine* e) {
   for (auto& g : e->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   for (void* p : e->allocs) cudaFree(p);
   if (e->host_flag) cudaFreeHost(e->host_flag);
+  if (e->host_stream) cudaFreeHost(e->host_stream);
   if (e->gen_stream) cudaStreamDestroy(e->gen_stream);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_t0) cudaEventDestroy(e->ev_t0);
@@ -822,7 +825,10 @@ int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream
   return SV_OK;
 }
 
-int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t* out_len, void* stream) {
+// The generate loop.  `cb` (optional) receives the new tokens of every row each time the host polls the device
+// (sv_generate_stream); with cb == NULL the code path is exactly sv_generate's.
+static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t* out_len, void* stream,
+                         sv_token_callback cb, void* cb_user) {
   if (!e || !p || !out_ids) return fail(e, SV_ERR_INVALID, "null argument");
   if (!e->prefilled) return fail(e, SV_ERR_STATE, "sv_generate needs sv_prefill first");
   if (e->host_cur_len != e->prefix_len) return fail(e, SV_ERR_STATE, "sv_generate must directly follow sv_prefill");
@@ -900,12 +906,35 @@ int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t*
   const int poll = p->poll_interval > 0 ? p->poll_interval : 16;
   const bool can_stop = p->eos_token_id >= 0 || p->n_stop_ids > 0;
   const bool mega = e->use_mega && fused_select;
+  // streaming: at every poll, tokens [emitted, step) of every row go to the callback through a pinned staging buffer
+  int emitted = 0;
+  bool cancelled = false;
+  auto emit_upto = [&](int upto) -> int {          // `st` must be idle (synchronised) when this is called
+    while (cb && emitted < upto) {
+      const int n = std::min(upto - emitted, kStreamChunk);
+      if (!e->host_stream) SV_CK(e, cudaMallocHost(reinterpret_cast<void**>(&e->host_stream), (size_t)e->d.max_batch * kStreamChunk * 4));
+      SV_CK(e, cudaMemcpy2DAsync(e->host_stream, (size_t)n * 4, e->out_ids + emitted, (size_t)e->d.max_len * 4, (size_t)n * 4, B,
+                                 cudaMemcpyDeviceToHost, st));
+      SV_CK(e, cudaStreamSynchronize(st));
+      if (cb(cb_user, e->host_stream, B, emitted, n) != 0) cancelled = true;
+      emitted += n;
+    }
+    return SV_OK;
+  };
+  auto poll_device = [&](bool& done_flag) -> int {  // done flag (+ step count when streaming), then the new tokens
+    SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->step, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // {step, done}
+    SV_CK(e, cudaStreamSynchronize(st));
+    done_flag = e->host_flag[1] != 0;
+    const int r = emit_upto(std::min(e->host_flag[0], max_new));
+    if (cancelled) done_flag = true;
+    return r;
+  };
   SV_CK(e, cudaEventRecord(e->ev_t0, st));
   int steps = 0;
   bool done = false;
   if (mega) {
     // persistent kernel: up to `chunk` whole tokens per cooperative launch, no host work in between
-    const int chunk = can_stop ? poll : 256;
+    const int chunk = (can_stop || cb) ? poll : 256;
     MegaLaunch m{};
     m.layers_dev = e->mega_layers; m.n_layer = e->d.n_layer; m.B = B; m.H = e->d.hidden; m.I = e->d.n_inner;
     m.n_head = e->d.n_head; m.n_kv = e->d.n_kv_head; m.qkv_cols = e->qkv_cols; m.vocab = e->d.vocab; m.tcap = e->tcap;
@@ -923,7 +952,10 @@ int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t*
       if (ce != cudaSuccess) return fail(e, SV_ERR_CUDA, "persistent decode launch failed: %s", cudaGetErrorString(ce));
       left -= m.nsteps;
       steps += m.nsteps;
-      if (can_stop && left > 0) {
+      if (cb && left > 0) {
+        const int r = poll_device(done);
+        if (r != SV_OK) return r;
+      } else if (can_stop && left > 0) {
         SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->done, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         SV_CK(e, cudaStreamSynchronize(st));
         done = e->host_flag[0] != 0;
@@ -934,7 +966,10 @@ int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t*
     SV_CK(e, cudaGraphLaunch(ge.exec, st));
     e->launches += ge.kernels;
     ++steps;
-    if (can_stop && (s % poll == 0)) {
+    if (cb && (s % poll == 0)) {
+      const int r = poll_device(done);
+      if (r != SV_OK) return r;
+    } else if (can_stop && (s % poll == 0)) {
       SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->done, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       SV_CK(e, cudaStreamSynchronize(st));
       done = e->host_flag[0] != 0;
@@ -945,6 +980,10 @@ int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t*
   SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->step, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   SV_CK(e, cudaStreamSynchronize(st));
   const int n_gen = std::min(e->host_flag[0], max_new);
+  if (cb) {
+    const int r = emit_upto(n_gen);
+    if (r != SV_OK) return r;
+  }
   SV_CK(e, cudaMemcpy2DAsync(out_ids, (size_t)max_new * 4, e->out_ids, (size_t)e->d.max_len * 4, (size_t)max_new * 4, B,
                              cudaMemcpyDeviceToDevice, st));
   if (out_len) launch_fill_i32(out_len, n_gen, B, st);
@@ -955,6 +994,16 @@ int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t*
   e->host_cur_len = e->prefix_len + std::max(0, n_gen - 1);
   e->prefilled = false;   // the cache now holds a finished generation; a new prefill is required
   return SV_OK;
+}
+
+int sv_generate(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t* out_len, void* stream) {
+  return generate_impl(e, p, out_ids, out_len, stream, nullptr, nullptr);
+}
+
+int sv_generate_stream(sv_engine* e, const sv_gen_params* p, int32_t* out_ids, int32_t* out_len, sv_token_callback on_tokens,
+                       void* user, void* stream) {
+  if (!on_tokens) return fail(e, SV_ERR_INVALID, "sv_generate_stream needs a callback (use sv_generate otherwise)");
+  return generate_impl(e, p, out_ids, out_len, stream, on_tokens, user);
 }
 
 int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_t batch, const int32_t* prompt_ids_host,

@@ -206,15 +206,37 @@ class Engine:
         with self._lock:
             self._ck(self._lib.sv_reorder_cache(self._h, C.c_void_p(idx.data_ptr()), _stream_ptr(self.device)))
 
-    def generate(self, params: GenerationParams) -> torch.Tensor:
-        """Run the decode loop after a prefill. Returns int32 [B, n_generated] (new tokens only)."""
+    def generate(self, params: GenerationParams, on_tokens=None) -> torch.Tensor:
+        """Run the decode loop after a prefill. Returns int32 [B, n_generated] (new tokens only).
+
+        `on_tokens(ids, first_step)` (optional) streams: it is called on this thread every `params.poll_interval` steps and
+        once at the end with a CPU int32 tensor `[B, n]` of the tokens generated since the previous call (`sv_generate_stream`);
+        returning a truthy value cancels the generation.  An exception raised by the callback cancels and is re-raised."""
         B, n = self._batch, int(params.max_new_tokens)
         out = torch.empty(B, max(n, 1), dtype=torch.int32, device=self.device)
         olen = torch.empty(B, dtype=torch.int32, device=self.device)
         cp = params.to_c()
-        with self._lock:
-            self._ck(self._lib.sv_generate(self._h, C.byref(cp), C.c_void_p(out.data_ptr()), C.c_void_p(olen.data_ptr()),
-                                           _stream_ptr(self.device)))
+        if on_tokens is None:
+            with self._lock:
+                self._ck(self._lib.sv_generate(self._h, C.byref(cp), C.c_void_p(out.data_ptr()), C.c_void_p(olen.data_ptr()),
+                                               _stream_ptr(self.device)))
+        else:
+            failure = []
+
+            def trampoline(_user, ids_ptr, batch, first_step, n_steps):
+                try:
+                    flat = torch.frombuffer(C.cast(ids_ptr, C.POINTER(C.c_int32 * (batch * n_steps))).contents, dtype=torch.int32)
+                    return 1 if on_tokens(flat.view(batch, n_steps).clone(), int(first_step)) else 0
+                except BaseException as exc:      # never let an exception unwind through the C frames
+                    failure.append(exc)
+                    return 1
+
+            cb = _lib.TOKEN_CALLBACK(trampoline)
+            with self._lock:
+                self._ck(self._lib.sv_generate_stream(self._h, C.byref(cp), C.c_void_p(out.data_ptr()), C.c_void_p(olen.data_ptr()),
+                                                      cb, None, _stream_ptr(self.device)))
+            if failure:
+                raise failure[0]
         n_gen = int(olen[0].item())
         return out[:, :n_gen]
 

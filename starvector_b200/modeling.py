@@ -163,10 +163,28 @@ class StarVectorStarCoder:
         params = self._gen_params(kwargs, prefix_len=self.query_length + prompt_ids.shape[1])
         num_beams = int(kwargs.get("num_beams", 2))                             # reference default (:234)
         if num_beams > 1:
+            if kwargs.get("streamer") is not None:                              # same rule and message as HF generate()
+                raise ValueError("`streamer` cannot be used with beam search (yet!). Make sure that `num_beams` is set to 1.")
             out = self._beam_generate(params, kwargs, num_beams, image=image, prompt_ids=prompt_ids)
             return torch.cat([prompt_ids.to(out.device), out.long()], dim=1)
         mb = self.engine.dims.max_batch
-        if image.shape[0] <= mb:
+        streamer = kwargs.get("streamer")                                       # serve/model_worker.py:131,172
+        if streamer is not None:
+            if image.shape[0] > mb:
+                raise ValueError(f"streaming needs the batch ({image.shape[0]}) to fit the engine's max_batch ({mb})")
+            self.engine.encode_images(image)
+            self.engine.prefill(prompt_ids)
+
+            def on_tokens(ids: torch.Tensor, first_step: int) -> bool:          # HF BaseStreamer protocol: put([B]) per step
+                for j in range(ids.shape[1]):
+                    streamer.put(ids[:, j].long())
+                return False
+
+            try:
+                out = self.engine.generate(params, on_tokens=on_tokens)
+            finally:
+                streamer.end()
+        elif image.shape[0] <= mb:
             self.engine.encode_images(image)
             self.engine.prefill(prompt_ids)
             out = self.engine.generate(params)

@@ -114,3 +114,42 @@ def test_more_images_than_max_batch_runs_in_groups(model):
     want = merge_generated([first, rest], tok("</svg>")["input_ids"], tok.pad_token_id)
     assert all6.shape[0] == 6 and torch.equal(all6[:, P:], want)
     assert len(m.model.generate_im2svg({"image": img}, **kw)) == 6
+
+
+def test_streamer_kwarg_streams_tokens(model):
+    """serve/model_worker.py:131-181: generate in a thread with `streamer=`, iterate the streamer for text."""
+    from threading import Thread
+
+    from transformers import TextIteratorStreamer
+
+    d, sd, m = model
+    tok = m.model.svg_transformer.tokenizer
+    P = len(tok("<svg")["input_ids"])
+    img = synthetic_images(d, 1, seed=1).cuda()
+    kw = dict(use_nucleus_sampling=False, num_beams=1, max_length=d.query_length + P + 20)
+
+    class Collect:
+        def __init__(self):
+            self.tokens, self.ended = [], False
+
+        def put(self, value):
+            self.tokens.append(value.clone())
+
+        def end(self):
+            self.ended = True
+
+    c = Collect()
+    ids = m.model.generate_im2svg_ids({"image": img}, streamer=c, **kw)
+    assert c.ended and all(t.shape == (1,) for t in c.tokens)
+    assert torch.equal(torch.stack(c.tokens, dim=1), ids[:, P:].cpu())
+    assert torch.equal(ids, m.model.generate_im2svg_ids({"image": img}, **kw))
+
+    streamer = TextIteratorStreamer(tok, skip_prompt=False, skip_special_tokens=True, timeout=60)
+    result = {}
+    thread = Thread(target=lambda: result.update(text=m.model.generate_im2svg(batch={"image": img}, streamer=streamer, **kw)))
+    thread.start()
+    pieces = [piece for piece in streamer]
+    thread.join()
+    assert "".join(pieces) == tok.decode(ids[0, P:].tolist(), skip_special_tokens=True) and len(result["text"]) == 1
+    with pytest.raises(ValueError):
+        m.model.generate_im2svg({"image": img}, streamer=Collect(), num_beams=2, max_length=kw["max_length"])
