@@ -15,6 +15,8 @@ run v2 python -m pytest tests/test_v2_gpu.py -q --tb=short -m gpu
 SV_DECODE=fused run v2_fused python -m pytest tests/test_v2_gpu.py -q --tb=short -m gpu
 run preprocess python -m pytest tests/test_preprocess_gpu.py -q --tb=short -m gpu
 run beam python -m pytest tests/test_beam_gpu.py -q --tb=short -m gpu
+run widening python -m pytest tests/test_widening_gpu.py -q --tb=short -m gpu
+SV_MEGA=1 run widening_mega python -m pytest tests/test_widening_gpu.py -q --tb=short -m gpu -k streaming
 run full_1b python -m pytest tests/test_full_1b_gpu.py -q --tb=short -m gpu
 run smoke python __graft_entry__.py --smoke
 TAILN=2 run bench_short python bench.py --steps 1 --warmup 1 --max-new-tokens 256 --no-cpu-baseline

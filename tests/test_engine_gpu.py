@@ -208,40 +208,3 @@ def test_errors_are_python_exceptions(tiny):
     eng.prefill(torch.tensor([PROMPT] * 2))
     with pytest.raises(ValueError):
         eng.generate(GenerationParams(max_new_tokens=10 ** 6, pad_token_id=0))
-
-
-def test_streaming_callback_sees_exactly_the_returned_tokens(tiny):
-    """sv_generate_stream: chunks arrive in order, their concatenation is the rectangle sv_generate returns; a truthy
-    return value cancels at the next poll; an exception in the callback cancels and propagates."""
-    d, sd, eng, o16, o32, img = tiny
-    p = GenerationParams(max_new_tokens=45, eos_token_id=None, pad_token_id=d.vocab - 4, poll_interval=8)
-
-    def run(cb=None, params=p):
-        eng.encode_images(img)
-        eng.prefill(torch.tensor([PROMPT] * 2))
-        return eng.generate(params, on_tokens=cb).cpu()
-
-    plain = run()
-    chunks = []
-    streamed = run(lambda ids, first: chunks.append((first, ids.clone())) and False)
-    assert torch.equal(streamed, plain)
-    assert [c[0] for c in chunks] == [sum(x[1].shape[1] for x in chunks[:i]) for i in range(len(chunks))]
-    assert len(chunks) >= 5 and torch.equal(torch.cat([c[1] for c in chunks], dim=1), plain)
-    # with a stop condition armed the same holds (row 0 stop after 7 tokens)
-    stop = plain[0, 4:7].tolist()
-    ps = GenerationParams(max_new_tokens=45, eos_token_id=None, pad_token_id=d.vocab - 4, poll_interval=4, stop_ids=stop)
-    want = run(params=ps)
-    chunks.clear()
-    got = run(lambda ids, first: chunks.append((first, ids.clone())) and False, params=ps)
-    assert torch.equal(got, want) and torch.equal(torch.cat([c[1] for c in chunks], dim=1), want)
-    # cancel
-    seen = []
-    cut = run(lambda ids, first: seen.append(ids.shape[1]) or sum(seen) >= 16)
-    assert 16 <= cut.shape[1] < 45 and torch.equal(cut, plain[:, : cut.shape[1]])
-
-    def boom(ids, first):
-        raise KeyError("from the callback")
-
-    with pytest.raises(KeyError):
-        run(boom)
-    assert torch.equal(run(), plain)                           # the engine is usable afterwards

@@ -78,78 +78,3 @@ def test_max_length_shorter_than_prefix_raises(model):
     d, sd, m = model
     with pytest.raises(ValueError, match="max_length"):
         m.generate_im2svg({"image": synthetic_images(d, 1)}, num_beams=1, max_length=d.query_length)   # < Q + P
-
-
-def test_grpo_num_return_sequences(model):
-    """starvector_base.py:261-286: G completions per image = rows repeated adjacently, sampled independently."""
-    d, sd, m = model
-    img = synthetic_images(d, 2, seed=1).cuda()
-    P = len(m.model.svg_transformer.tokenizer("<svg")["input_ids"])
-    kw = dict(max_length=d.query_length + P + 10)
-    two = m.model.generate_im2svg_grpo({"image": img}, use_nucleus_sampling=False, num_return_sequences=2, **kw)
-    assert two["outputs"].shape[0] == 4 and len(two["raw_svg"]) == 4
-    assert torch.equal(two["outputs"][0], two["outputs"][1]) and torch.equal(two["outputs"][2], two["outputs"][3])
-    one = m.model.generate_im2svg_grpo({"image": img}, use_nucleus_sampling=False, **kw)
-    assert torch.equal(one["outputs"], two["outputs"][::2])
-    assert two["inputs_embeds"].shape == (2, d.query_length + P, d.hidden)
-    s = m.model.generate_im2svg_grpo({"image": img[:1]}, num_return_sequences=4, temperature=2.0, top_p=1.0, **kw)
-    assert s["outputs"].shape[0] == 4
-    assert len({tuple(r.tolist()) for r in s["outputs"]}) >= 3          # independent samples per copy
-    with pytest.raises(ValueError):
-        m.model.generate_im2svg_grpo({"image": img}, num_return_sequences=3, **kw)      # 6 rows > max_batch 4
-
-
-def test_more_images_than_max_batch_runs_in_groups(model):
-    """6 images on an engine that holds 4: two groups, merged with the row-0 stop rule of the sharded path."""
-    from starvector_b200.parallel import merge_generated
-
-    d, sd, m = model
-    img = synthetic_images(d, 6, seed=4).cuda()
-    tok = m.model.svg_transformer.tokenizer
-    P = len(tok("<svg")["input_ids"])
-    kw = dict(use_nucleus_sampling=False, num_beams=1, max_length=d.query_length + P + 12)
-    all6 = m.model.generate_im2svg_ids({"image": img}, **kw)
-    first = m.model.generate_im2svg_ids({"image": img[:4]}, **kw)[:, P:]
-    rest = m.model.generate_im2svg_ids({"image": img[4:]}, stop_ids=(), **kw)[:, P:]
-    want = merge_generated([first, rest], tok("</svg>")["input_ids"], tok.pad_token_id)
-    assert all6.shape[0] == 6 and torch.equal(all6[:, P:], want)
-    assert len(m.model.generate_im2svg({"image": img}, **kw)) == 6
-
-
-def test_streamer_kwarg_streams_tokens(model):
-    """serve/model_worker.py:131-181: generate in a thread with `streamer=`, iterate the streamer for text."""
-    from threading import Thread
-
-    from transformers import TextIteratorStreamer
-
-    d, sd, m = model
-    tok = m.model.svg_transformer.tokenizer
-    P = len(tok("<svg")["input_ids"])
-    img = synthetic_images(d, 1, seed=1).cuda()
-    kw = dict(use_nucleus_sampling=False, num_beams=1, max_length=d.query_length + P + 20)
-
-    class Collect:
-        def __init__(self):
-            self.tokens, self.ended = [], False
-
-        def put(self, value):
-            self.tokens.append(value.clone())
-
-        def end(self):
-            self.ended = True
-
-    c = Collect()
-    ids = m.model.generate_im2svg_ids({"image": img}, streamer=c, **kw)
-    assert c.ended and all(t.shape == (1,) for t in c.tokens)
-    assert torch.equal(torch.stack(c.tokens, dim=1), ids[:, P:].cpu())
-    assert torch.equal(ids, m.model.generate_im2svg_ids({"image": img}, **kw))
-
-    streamer = TextIteratorStreamer(tok, skip_prompt=False, skip_special_tokens=True, timeout=60)
-    result = {}
-    thread = Thread(target=lambda: result.update(text=m.model.generate_im2svg(batch={"image": img}, streamer=streamer, **kw)))
-    thread.start()
-    pieces = [piece for piece in streamer]
-    thread.join()
-    assert "".join(pieces) == tok.decode(ids[0, P:].tolist(), skip_special_tokens=True) and len(result["text"]) == 1
-    with pytest.raises(ValueError):
-        m.model.generate_im2svg({"image": img}, streamer=Collect(), num_beams=2, max_length=kw["max_length"])
