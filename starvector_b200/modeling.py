@@ -143,15 +143,17 @@ class StarVectorStarCoder:
 
     def _beam_generate(self, params: GenerationParams, kw: Dict[str, Any], num_beams: int, image=None, prompt_ids=None,
                        inputs_embeds=None) -> torch.Tensor:
-        """num_beams > 1 (the reference default is 2, starvector_base.py:234): beam search / beam-sample with
-        `early_stopping=True` (:292) and the caller's `length_penalty` — bookkeeping in beam_search.py."""
+        """num_beams > 1 (the reference default is 2, starvector_base.py:234): beam search / beam-sample with the
+        caller's `length_penalty`; `early_stopping=True` for v1 (:292), HF's default False for v2
+        (starvector_v2.py:53-57) — bookkeeping in beam_search.py."""
         from .beam_search import beam_search
 
         return beam_search(
             self.engine, image, prompt_ids, inputs_embeds=inputs_embeds, num_beams=num_beams,
             max_new_tokens=params.max_new_tokens, do_sample=params.do_sample, temperature=params.temperature,
             top_p=params.top_p, repetition_penalty=params.repetition_penalty,
-            length_penalty=float(kw.get("length_penalty", 1.0)), early_stopping=True,
+            length_penalty=float(kw.get("length_penalty", 1.0)),
+            early_stopping=not self.v2,       # v1 passes early_stopping=True (:292); v2's specific kwargs are {} -> HF default False
             eos_token_id=params.eos_token_id, pad_token_id=params.pad_token_id, stop_ids=params.stop_ids, seed=params.seed)
 
     # -- the path ------------------------------------------------------------------------

@@ -67,3 +67,24 @@ def test_beam_search_matches_hf(setup, nb, lp, rp, stop):
                       repetition_penalty=rp, length_penalty=lp, early_stopping=True, eos_token_id=0,
                       pad_token_id=d.vocab - 4, stop_ids=stop_ids)
     assert got.shape == ref.shape and torch.equal(got, ref), (got.tolist(), ref.tolist())
+
+
+@pytest.mark.parametrize("nb,lp", [(2, 1.0), (3, 1.0), (2, -1.0)])
+def test_beam_search_without_early_stopping_matches_hf(setup, nb, lp):
+    """v2 passes no `early_stopping` (starvector_v2.py:53-57 returns {}), so HF's default False applies: the loop runs on
+    until the best running beam can no longer beat the worst finished one."""
+    import warnings
+
+    d, o, img = setup
+    n_new = 14
+    emb, mask, _ = o.prepare_generation_inputs(img, PROMPT)
+    kw = o.generation_kwargs({"inputs_embeds": emb, "attention_mask": mask, "use_nucleus_sampling": False, "num_beams": nb,
+                              "length_penalty": lp, "max_length": d.query_length + len(PROMPT) + n_new}, ())
+    kw.pop("top_p"); kw.pop("temperature")
+    kw["early_stopping"] = False
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = o.llm.generate(**kw)
+    got = beam_search(OracleBackedEngine(o), img, torch.tensor([PROMPT] * 2), num_beams=nb, max_new_tokens=n_new,
+                      length_penalty=lp, early_stopping=False, eos_token_id=0, pad_token_id=d.vocab - 4)
+    assert got.shape == ref.shape and torch.equal(got, ref), (got.tolist(), ref.tolist())
