@@ -42,7 +42,7 @@ double bicubic_filter(double x) {
 
 struct Coeffs {
   int ksize = 0;
-  std::vector<int32_t> data;   // bounds[out][2] (first tap, tap count) followed by taps[out][ksize]
+  std::vector<int32_t> data;   // bounds[out][2] (first tap, tap count) followed by taps[ksize][out] (tap-major)
 };
 
 Coeffs precompute_coeffs(int in_size, int out_size) {
@@ -68,10 +68,10 @@ Coeffs precompute_coeffs(int in_size, int out_size) {
       w[x] = bicubic_filter((x + xmin - center + 0.5) * ss);
       ww += w[x];
     }
-    int32_t* k = taps + (size_t)xx * c.ksize;
     for (int x = 0; x < xmax; ++x) {
       const double v = ww != 0.0 ? w[x] / ww : w[x];
-      k[x] = v < 0 ? (int)(-0.5 + v * (1 << svpre::kPrecisionBits)) : (int)(0.5 + v * (1 << svpre::kPrecisionBits));
+      taps[(size_t)x * out_size + xx] =
+          v < 0 ? (int)(-0.5 + v * (1 << svpre::kPrecisionBits)) : (int)(0.5 + v * (1 << svpre::kPrecisionBits));
     }
     bounds[2 * xx] = xmin;
     bounds[2 * xx + 1] = xmax;
@@ -265,7 +265,9 @@ int sv_resample_coeffs_host(int32_t in_size, int32_t out_size, int32_t* ksize, i
   if (!bounds && !taps) return SV_OK;
   if (!bounds || !taps || (int64_t)taps_capacity < (int64_t)out_size * c.ksize) return SV_ERR_INVALID;
   std::memcpy(bounds, c.data.data(), sizeof(int32_t) * 2 * out_size);
-  std::memcpy(taps, c.data.data() + 2 * (size_t)out_size, sizeof(int32_t) * (size_t)out_size * c.ksize);
+  const int32_t* tm = c.data.data() + 2 * (size_t)out_size;          // stored tap-major; the export is [out][ksize]
+  for (int xx = 0; xx < out_size; ++xx)
+    for (int t = 0; t < c.ksize; ++t) taps[(size_t)xx * c.ksize + t] = tm[(size_t)t * out_size + xx];
   return SV_OK;
 }
 

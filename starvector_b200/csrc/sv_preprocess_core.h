@@ -29,7 +29,8 @@ struct ImageMeta {
   int32_t in_w, in_h;   // the image the resample sees: (S,S) with S=max(w,h) when padded, else (w,h)
   int32_t pad_left, pad_top;
   int32_t alpha_white;  // 1: RGBA is pasted on white with alpha as mask; 0: alpha is dropped
-  int32_t kx_off, ky_off, ksize_x, ksize_y;      // int32 offsets into the coefficient arena: bounds[out][2] then taps[out][ksize]
+  int32_t kx_off, ky_off, ksize_x, ksize_y;      // int32 offsets into the coefficient arena: bounds[out][2] then taps[ksize][out]
+                                                 // (tap-major: the lanes of a warp, adjacent outputs, read adjacent words)
 };
 
 SV_HD int muldiv255(int a, int b) {
@@ -66,12 +67,12 @@ SV_HD int clip8(int acc) {
 SV_HD uint32_t horizontal_pixel(const uint8_t* __restrict__ arena, const int32_t* __restrict__ coeffs, const ImageMeta& im,
                                 int out_w, int y, int xx) {
   const int32_t* bounds = coeffs + im.kx_off;
-  const int32_t* taps = bounds + 2 * out_w + (int64_t)xx * im.ksize_x;
+  const int32_t* taps = bounds + 2 * out_w + xx;
   const int x0 = bounds[2 * xx], n = bounds[2 * xx + 1];
   int r = 1 << (kPrecisionBits - 1), g = r, b = r;
   for (int t = 0; t < n; ++t) {
     const uint32_t px = fetch_rgb(arena, im, y, x0 + t);
-    const int k = taps[t];
+    const int k = taps[(int64_t)t * out_w];
     r += (int)(px & 255u) * k;
     g += (int)((px >> 8) & 255u) * k;
     b += (int)((px >> 16) & 255u) * k;
@@ -83,13 +84,13 @@ SV_HD uint32_t horizontal_pixel(const uint8_t* __restrict__ arena, const int32_t
 SV_HD void vertical_pixel(const uint32_t* __restrict__ tmp, const int32_t* __restrict__ coeffs, const ImageMeta& im, int out_w,
                           int out_h, int yy, int xx, int rgb[3]) {
   const int32_t* bounds = coeffs + im.ky_off;
-  const int32_t* taps = bounds + 2 * out_h + (int64_t)yy * im.ksize_y;
+  const int32_t* taps = bounds + 2 * out_h + yy;
   const int y0 = bounds[2 * yy], n = bounds[2 * yy + 1];
   const uint32_t* col = tmp + im.tmp_off + (int64_t)y0 * out_w + xx;
   int r = 1 << (kPrecisionBits - 1), g = r, b = r;
   for (int t = 0; t < n; ++t) {
     const uint32_t px = col[(int64_t)t * out_w];
-    const int k = taps[t];
+    const int k = taps[(int64_t)t * out_h];
     r += (int)(px & 255u) * k;
     g += (int)((px >> 8) & 255u) * k;
     b += (int)((px >> 16) & 255u) * k;
