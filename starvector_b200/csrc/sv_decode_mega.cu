@@ -673,7 +673,16 @@ SV_DEVINL void select_phase(const Ctx& cx, int ntiles) {
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) decode_mega_kernel(const Args a) {
+// REALLOC = true is the warp-specialised register split (opt-in SV_MEGA=2): the CTA is launched with three warpgroups
+// (384 threads x 168 registers = the whole register file), warpgroup 2 (the producer warp + three idle warps) gives
+// registers back with `setmaxnreg.dec` and the two consumer warpgroups take them with `setmaxnreg.inc`
+// (128 x (168-56) = 256 x (224-168)), so the GEMV/attention code is no longer compiled against the 168-register cap that
+// nine equal warps impose (one SM sub-partition would have to hold three of them).
+constexpr int NTHREADS_REALLOC = NCT + 128;
+constexpr int REGS_PRODUCER = 56, REGS_CONSUMER = 224;
+
+template <bool REALLOC>
+__global__ void __launch_bounds__(REALLOC ? NTHREADS_REALLOC : NTHREADS, 1) decode_mega_kernel(const Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -690,7 +699,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_mega_kernel(const Args a) 
   __syncthreads();
 
   const int qkv_n = a.qkv_cols;
-  if (warp == NWC) {
+  if (warp >= NWC) {
+    if constexpr (REALLOC) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+      if (warp > NWC) return;          // the other three warps of the producer warpgroup only exist to hand registers over
+    }
     // =========================== producer ===========================
     for (int s = 0; s < a.nsteps; ++s) {
       for (int l = 0; l < a.n_layer; ++l) {
@@ -705,6 +718,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_mega_kernel(const Args a) 
     return;   // in-flight bulk copies are all consumed (and thus complete) before the consumers exit
   }
   // =========================== consumers ===========================
+  if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
   Ctx cx;
   cx.a = &a; cx.smem = smem; cx.cta = cta; cx.ncta = ncta; cx.warp = warp; cx.lane = lane; cx.g = lane >> 2; cx.t = lane & 3;
   cx.red = reinterpret_cast<float*>(smem + OFF_RED);
@@ -807,24 +821,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_ring_kernel(const RingGemvAr
 
 // ---- host side
 static int g_mega_ncta = 0;
+static bool g_mega_realloc_ok = false;
 static char g_mega_why[256] = "decode_mega_init not called";
 const char* decode_mega_status() { return g_mega_why; }
 
 cudaError_t decode_mega_init() {
-  cudaError_t e = cudaFuncSetAttribute(mega::decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(mega::decode_mega_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        mega::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  int dev = 0, nsm = 0, per_sm = 0, coop = 0;
+  e = cudaFuncSetAttribute(mega::decode_mega_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  int dev = 0, nsm = 0, per_sm = 0, per_sm_realloc = 0, coop = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega::decode_mega_kernel, mega::NTHREADS, mega::SMEM_BYTES);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega::decode_mega_kernel<false>, mega::NTHREADS, mega::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_realloc, mega::decode_mega_kernel<true>, mega::NTHREADS_REALLOC,
+                                                    mega::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   g_mega_ncta = (coop && per_sm >= 1) ? nsm : 0;
-  snprintf(g_mega_why, sizeof(g_mega_why), "sms=%d coop=%d blocks_per_sm=%d smem=%d threads=%d -> ncta=%d", nsm, coop,
-           per_sm, mega::SMEM_BYTES, mega::NTHREADS, g_mega_ncta);
+  g_mega_realloc_ok = coop && per_sm_realloc >= 1;
+  snprintf(g_mega_why, sizeof(g_mega_why), "sms=%d coop=%d blocks_per_sm=%d (setmaxnreg variant: %d) smem=%d threads=%d -> ncta=%d",
+           nsm, coop, per_sm, per_sm_realloc, mega::SMEM_BYTES, mega::NTHREADS, g_mega_ncta);
   return cudaSuccess;
 }
+bool decode_mega_realloc_supported() { return g_mega_realloc_ok; }
 int decode_mega_ncta() { return g_mega_ncta; }
 bool decode_mega_supported(int H, int I, int head_dim, int max_batch) {
   auto okk = [](int K) { return K % 32 == 0 && (K <= mega::KS_MAX ? true : K % mega::KS_MAX == 0); };
@@ -844,8 +866,12 @@ cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(m.barrier_ctr, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   void* args[] = {&a};
-  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mega::decode_mega_kernel), dim3(g_mega_ncta),
-                                  dim3(mega::NTHREADS), args, mega::SMEM_BYTES, st);
+  if (m.realloc)
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mega::decode_mega_kernel<true>), dim3(g_mega_ncta),
+                                    dim3(mega::NTHREADS_REALLOC), args, mega::SMEM_BYTES, st);
+  else
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mega::decode_mega_kernel<false>), dim3(g_mega_ncta),
+                                    dim3(mega::NTHREADS), args, mega::SMEM_BYTES, st);
   count_launch();
   return e;
 }

@@ -76,6 +76,7 @@ struct sv_engine {
   bf16 *d_x, *d_ln, *d_qkv, *d_attn, *d_h, *d_last, *logits;
   float *logits_f32, *attn_partial, *amax_val;
   int *amax_idx, *attn_counters;
+  bool mega_realloc = false;
   bool fused_decode = true, use_pdl = true, use_mega = false, use_ring = true, use_cluster_attn = true, use_l2_prefetch = false;
   MegaLayer* mega_layers = nullptr;
   unsigned int* mega_barrier = nullptr;
@@ -623,7 +624,8 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   const char* pdl = getenv("SV_PDL");             // "0" = plain stream order between decode kernels
   if (pdl && !strcmp(pdl, "0")) e->use_pdl = false;
   const char* mg = getenv("SV_MEGA");             // "1" = persistent multi-token kernel instead of the per-phase CUDA graph
-  e->use_mega = mg && !strcmp(mg, "1");           // (opt-in until it beats the graph path: DESIGN.md "decode modes")
+  e->use_mega = mg && (!strcmp(mg, "1") || !strcmp(mg, "2"));   // (opt-in until it beats the graph path: DESIGN.md "decode modes")
+  e->mega_realloc = mg && !strcmp(mg, "2");       // "2" = the same kernel with setmaxnreg register reallocation
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
   const char* at = getenv("SV_ATTN");             // "ticket" = global-scratch + atomic-ticket merge instead of the cluster/DSMEM merge
   if (at && !strcmp(at, "ticket")) e->use_cluster_attn = false;
@@ -664,6 +666,7 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
       return fail(nullptr, SV_ERR_CUDA, "persistent decode kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (!decode_mega_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch) || !e->fused_decode) e->use_mega = false;
+    if (e->mega_realloc && !decode_mega_realloc_supported()) e->mega_realloc = false;
   }
   if (attention_decode_fused_init() != cudaSuccess || attention_decode_cluster_init() != cudaSuccess) {
     sv_engine_destroy(e);
@@ -944,6 +947,7 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
     m.state = e->state; m.params = e->params; m.seen = e->seen; m.next_ids = e->next_ids; m.out_ids = e->out_ids;
     m.barrier_ctr = e->mega_barrier; m.att_ncta = nsplit;
     m.dbg = e->mega_debug ? e->mega_dbg : nullptr;
+    m.realloc = e->mega_realloc;
     if (e->mega_debug) cudaMemsetAsync(e->mega_dbg, 0, 1024 * sizeof(long long), st);
     int left = max_new - 1;
     while (left > 0 && !done) {
@@ -1070,7 +1074,7 @@ const char* sv_engine_describe(sv_engine* e) {
   if (!e) return "";
   char buf[512];
   snprintf(buf, sizeof(buf), "decode=%s attn=%s pdl=%d l2pf=%d linear_impl=%d mega[%s]",
-           !e->fused_decode ? "legacy-kernels" : (e->use_mega ? "persistent-kernel" : (e->use_ring ? "ring-gemv-graph" : "reg-gemv-graph")),
+           !e->fused_decode ? "legacy-kernels" : (e->use_mega ? (e->mega_realloc ? "persistent-kernel-setmaxnreg" : "persistent-kernel") : (e->use_ring ? "ring-gemv-graph" : "reg-gemv-graph")),
            e->use_cluster_attn ? "cluster-dsmem" : "ticket", (int)e->use_pdl, (int)e->use_l2_prefetch, e->linear_impl, decode_mega_status());
   e->describe = buf;
   return e->describe.c_str();

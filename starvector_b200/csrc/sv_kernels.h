@@ -138,6 +138,7 @@ struct MegaLaunch {
   unsigned int* barrier_ctr;
   int nsteps, att_ncta;
   long long* dbg;
+  bool realloc;        // SV_MEGA=2: three warpgroups with setmaxnreg register reallocation
 };
 // one-phase weight-ring GEMV (same device code as the persistent kernel's GEMV phases)
 struct RingGemvLaunch {
@@ -162,6 +163,7 @@ cudaError_t decode_mega_init();
 int decode_mega_ncta();
 const char* decode_mega_status();
 bool decode_mega_supported(int H, int I, int head_dim, int max_batch);
+bool decode_mega_realloc_supported();
 cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st);
 
 }  // namespace sv
