@@ -829,17 +829,21 @@ cudaError_t decode_mega_init() {
   cudaError_t e = cudaFuncSetAttribute(mega::decode_mega_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        mega::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(mega::decode_mega_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mega::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
+  // the experimental variant must never make engine creation fail: its errors only disable it
+  bool realloc_attr_ok = cudaFuncSetAttribute(mega::decode_mega_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              mega::SMEM_BYTES) == cudaSuccess;
+  if (!realloc_attr_ok) cudaGetLastError();
   int dev = 0, nsm = 0, per_sm = 0, per_sm_realloc = 0, coop = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega::decode_mega_kernel<false>, mega::NTHREADS, mega::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_realloc, mega::decode_mega_kernel<true>, mega::NTHREADS_REALLOC,
-                                                    mega::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
+  if (!realloc_attr_ok || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_realloc, mega::decode_mega_kernel<true>,
+                                                                         mega::NTHREADS_REALLOC, mega::SMEM_BYTES) != cudaSuccess) {
+    per_sm_realloc = 0;
+    cudaGetLastError();
+  }
   g_mega_ncta = (coop && per_sm >= 1) ? nsm : 0;
   g_mega_realloc_ok = coop && per_sm_realloc >= 1;
   snprintf(g_mega_why, sizeof(g_mega_why), "sms=%d coop=%d blocks_per_sm=%d (setmaxnreg variant: %d) smem=%d threads=%d -> ncta=%d",
