@@ -15,6 +15,7 @@ SV_DECODE=legacy run engine_legacy python -m pytest tests/test_engine_gpu.py -q 
 run v2 python -m pytest tests/test_v2_gpu.py -q --tb=short -m gpu
 SV_DECODE=fused run v2_fused python -m pytest tests/test_v2_gpu.py -q --tb=short -m gpu
 run preprocess python -m pytest tests/test_preprocess_gpu.py -q --tb=short -m gpu
+SV_STEP_GRAPH=1 run step_graph python -m pytest tests/test_engine_gpu.py tests/test_beam_gpu.py -q --tb=short -m gpu
 run beam python -m pytest tests/test_beam_gpu.py -q --tb=short -m gpu
 run widening python -m pytest tests/test_widening_gpu.py -q --tb=short -m gpu
 SV_MEGA=1 run widening_mega python -m pytest tests/test_widening_gpu.py -q --tb=short -m gpu -k streaming

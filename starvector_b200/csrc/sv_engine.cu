@@ -77,6 +77,7 @@ struct sv_engine {
   float *logits_f32, *attn_partial, *amax_val;
   int *amax_idx, *attn_counters;
   bool mega_realloc = false;
+  bool step_graph = false;          // SV_STEP_GRAPH=1: sv_decode_step replays a captured graph (opt-in)
   bool fused_decode = true, use_pdl = true, use_mega = false, use_ring = true, use_cluster_attn = true, use_l2_prefetch = false;
   MegaLayer* mega_layers = nullptr;
   unsigned int* mega_barrier = nullptr;
@@ -627,6 +628,7 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   e->use_mega = mg && (!strcmp(mg, "1") || !strcmp(mg, "2"));   // (opt-in until it beats the graph path: DESIGN.md "decode modes")
   e->mega_realloc = mg && !strcmp(mg, "2");       // "2" = the same kernel with setmaxnreg register reallocation
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
+  { const char* sg = getenv("SV_STEP_GRAPH"); e->step_graph = sg && !strcmp(sg, "1"); }
   const char* at = getenv("SV_ATTN");             // "ticket" = global-scratch + atomic-ticket merge instead of the cluster/DSMEM merge
   if (at && !strcmp(at, "ticket")) e->use_cluster_attn = false;
   const char* pf = getenv("SV_L2_PREFETCH");      // "1" = prefetch the next GEMV's weights into L2 (measured: no gain, off)
@@ -817,11 +819,46 @@ int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream
   SV_CK(e, cudaSetDevice(e->device));
   LaunchScope scope(e);
   cudaStream_t st = (cudaStream_t)stream;
-  int r = e->fused_decode
-              ? run_decode_layers_fused(e, ids, e->cur_batch, attention_decode_fused_ncta(e->host_cur_len + 1), e->use_pdl, st)
-              : run_decode_layers(e, ids, e->cur_batch, nsplit_for(e, e->host_cur_len + 1), st);
-  if (r != SV_OK) return r;
-  launch_advance_len(e->state, st);
+  int r = SV_OK;
+  if (e->step_graph && e->fused_decode) {
+    // opt-in (SV_STEP_GRAPH=1): the step as ONE replayed graph instead of ~122 eager launches — what beam search and
+    // teacher forcing pay per token.  ids go through the engine's own buffer so that the captured pointers are stable.
+    const int B = e->cur_batch, nsplit = attention_decode_fused_ncta(e->host_cur_len + 1);
+    SV_CK(e, cudaMemcpyAsync(e->next_ids, ids, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    const long long key = 50000000LL + (long long)B * 100000 + nsplit * 8 + (e->use_pdl ? 4 : 0);
+    GraphEntry& ge = e->graphs[key];
+    for (int attempt = 0; attempt < 2 && !ge.exec; ++attempt) {
+      const bool pdl = e->use_pdl && attempt == 0;
+      cudaStream_t cs = e->gen_stream;
+      int64_t counted = 0;
+      g_launch_counter = &counted;
+      cudaGraph_t graph = nullptr;
+      SV_CK(e, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      r = run_decode_layers_fused(e, e->next_ids, B, nsplit, pdl, cs);
+      launch_advance_len(e->state, cs);
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      g_launch_counter = &e->launches;
+      if (r != SV_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        ge.exec = nullptr;
+        cudaGetLastError();
+        if (!pdl) SV_CK(e, ce);
+        e->use_pdl = false;
+        continue;
+      }
+      ge.kernels = (int)counted;
+    }
+    SV_CK(e, cudaGraphLaunch(ge.exec, st));
+    e->launches += ge.kernels;
+  } else {
+    r = e->fused_decode
+            ? run_decode_layers_fused(e, ids, e->cur_batch, attention_decode_fused_ncta(e->host_cur_len + 1), e->use_pdl, st)
+            : run_decode_layers(e, ids, e->cur_batch, nsplit_for(e, e->host_cur_len + 1), st);
+    if (r != SV_OK) return r;
+    launch_advance_len(e->state, st);
+  }
   if (logits) launch_logits_to_float(e->logits, logits, (int64_t)e->cur_batch * e->d.vocab, st);
   SV_CK(e, cudaGetLastError());
   e->host_cur_len += 1;
