@@ -153,3 +153,21 @@ def test_plan_rejects_bad_images():
         imgs = (_lib.ImageU8 * 1)(bad)
         assert lib.sv_preproc_plan_host(C.byref(_desc()), imgs, 1, None, 0, sizes) == _lib.SV_ERR_INVALID
         assert lib.sv_preproc_last_error(None)
+
+
+def test_processor_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a machine without a usable sm_100 device the constructor raises (and says why)."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from starvector_b200.preprocess import ImageTrainProcessor, _as_u8_hwc
+
+    with pytest.raises(_lib.EngineError, match="no CPU fallback"):
+        ImageTrainProcessor(size=224)
+    # host-side input validation does not need the device
+    with pytest.raises(ValueError):
+        _as_u8_hwc(np.zeros((4, 4), np.uint8))
+    with pytest.raises(ValueError):
+        _as_u8_hwc("not an image")
+    view = np.zeros((8, 12, 4), np.uint8)[:, 2:9]
+    assert _as_u8_hwc(view).strides == view.strides            # row-strided views are passed through, not copied
+    assert _as_u8_hwc(np.zeros((8, 12, 4), np.uint8)[:, ::2]).flags["C_CONTIGUOUS"]      # pixel-strided ones are copied
