@@ -110,3 +110,30 @@ def test_state_dict_names_follow_reference_tree():
     assert "model.image_encoder.visual_encoder.transformer.resblocks.0.attn.in_proj_weight" in sd
     assert "model.image_projection.norm.weight" in sd
     assert sd["model.svg_transformer.transformer.lm_head.weight"] is sd["model.svg_transformer.transformer.transformer.wte.weight"]
+
+
+def test_real_tokenizer_directory_is_prepared_like_the_reference(tmp_path):
+    """llm/starcoder.py:40-53: eos/pad added when missing, the three start tokens appended; the facade's calls on it."""
+    from tokenizers import Tokenizer, decoders, models, pre_tokenizers, trainers
+    from transformers import PreTrainedTokenizerFast
+
+    from starvector_b200.tokenizer import load_tokenizer
+
+    tk = Tokenizer(models.BPE(unk_token="<unk>"))
+    tk.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tk.decoder = decoders.ByteLevel()
+    corpus = ['<svg xmlns="http://www.w3.org/2000/svg" viewBox="0 0 24 24"><path d="M12 2L2 7l10 5 10-5z"/></svg>'] * 4
+    tk.train_from_iterator(corpus, trainers.BpeTrainer(vocab_size=120, special_tokens=["<unk>"]))
+    PreTrainedTokenizerFast(tokenizer_object=tk, unk_token="<unk>").save_pretrained(str(tmp_path))
+    tok = load_tokenizer(str(tmp_path), vocab_size=500)
+    assert not isinstance(tok, SyntheticTokenizer)
+    assert tok.eos_token == "[EOS]" and tok.pad_token == "[PAD]" and tok.eos_token_id != tok.pad_token_id
+    for t in ("<svg-start>", "<image-start>", "<caption-start>"):
+        assert len(tok.encode(t)) == 1
+    stop = tok("</svg>", add_special_tokens=False)["input_ids"]                 # starvector_base.py:226
+    prompt = tok(["<svg"] * 2, add_special_tokens=False, return_tensors="pt", padding="longest", truncation=True)["input_ids"]
+    assert prompt.shape[0] == 2 and 1 <= len(stop) <= 8
+    ids = prompt[0].tolist() + tok(' viewBox="0 0 24 24">')["input_ids"] + stop + [tok.eos_token_id, tok.pad_token_id]
+    assert tok.batch_decode([ids], skip_special_tokens=True)[0] == '<svg viewBox="0 0 24 24"></svg>'
+    assert isinstance(load_tokenizer(None, 500), SyntheticTokenizer)
+    assert isinstance(load_tokenizer(str(tmp_path / "missing"), 500), SyntheticTokenizer)
