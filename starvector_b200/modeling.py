@@ -230,6 +230,35 @@ class StarVectorStarCoder:
                 "outputs": ids, "inputs_embeds": inputs_embeds}
 
 
+def read_checkpoint(path: str):
+    """`(StarVectorConfig, state_dict)` from a local HF-style directory: config.json + every *.safetensors shard, or
+    pytorch_model.bin.  Tensors stay on the CPU in their stored dtype; the engine converts to bf16 at load."""
+    config = StarVectorConfig.from_pretrained(path)
+    sd: Dict[str, torch.Tensor] = {}
+    files = sorted(f for f in os.listdir(path) if f.endswith(".safetensors"))
+    if files:
+        from safetensors.torch import load_file
+
+        for f in files:
+            sd.update(load_file(os.path.join(path, f)))
+    elif os.path.exists(os.path.join(path, "pytorch_model.bin")):
+        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+    else:
+        raise FileNotFoundError(f"no *.safetensors / pytorch_model.bin under {path}")
+    return config, sd
+
+
+def write_checkpoint(path: str, config: StarVectorConfig, state_dict: Dict[str, torch.Tensor]) -> None:
+    """config.json + model.safetensors; the tied `lm_head.weight` is not stored twice (train/util.py:68-77)."""
+    from safetensors.torch import save_file
+
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(config.to_dict(), f, indent=1)
+    save_file({k: v.contiguous() for k, v in state_dict.items() if not k.endswith("lm_head.weight")},
+              os.path.join(path, "model.safetensors"))
+
+
 class StarVectorForCausalLM:
     """`StarVectorForCausalLM` facade (starvector_arch.py:133-193) — not an nn.Module: weights live in the engine."""
 
@@ -270,28 +299,11 @@ class StarVectorForCausalLM:
     def from_pretrained(cls, path: str, torch_dtype: Any = None, device: int = 0, max_batch: int = 8,
                         max_len: Optional[int] = None, **kw) -> "StarVectorForCausalLM":
         """Load a LOCAL checkpoint directory (config.json + *.safetensors / pytorch_model.bin).  No hub access."""
-        config = StarVectorConfig.from_pretrained(path)
-        sd: Dict[str, torch.Tensor] = {}
-        files = sorted(f for f in os.listdir(path) if f.endswith(".safetensors"))
-        if files:
-            from safetensors.torch import load_file
-
-            for f in files:
-                sd.update(load_file(os.path.join(path, f)))
-        elif os.path.exists(os.path.join(path, "pytorch_model.bin")):
-            sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
-        else:
-            raise FileNotFoundError(f"no *.safetensors / pytorch_model.bin under {path}")
+        config, sd = read_checkpoint(path)
         return cls(config, sd, device=device, max_batch=max_batch, max_len=max_len, tokenizer_path=path)
 
     def save_pretrained(self, path: str, state_dict: Dict[str, torch.Tensor]) -> None:
-        from safetensors.torch import save_file
-
-        os.makedirs(path, exist_ok=True)
-        with open(os.path.join(path, "config.json"), "w") as f:
-            json.dump(self.config.to_dict(), f, indent=1)
-        save_file({k: v.contiguous() for k, v in state_dict.items() if not k.endswith("lm_head.weight")},
-                  os.path.join(path, "model.safetensors"))
+        write_checkpoint(path, self.config, state_dict)
 
     # -- nn.Module-ish no-ops the callers use (quickstart.py:11-12) ------------------------
     def cuda(self, *a, **k): return self

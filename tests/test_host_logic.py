@@ -137,3 +137,30 @@ def test_real_tokenizer_directory_is_prepared_like_the_reference(tmp_path):
     assert tok.batch_decode([ids], skip_special_tokens=True)[0] == '<svg viewBox="0 0 24 24"></svg>'
     assert isinstance(load_tokenizer(None, 500), SyntheticTokenizer)
     assert isinstance(load_tokenizer(str(tmp_path / "missing"), 500), SyntheticTokenizer)
+
+
+def test_checkpoint_directory_round_trip(tmp_path):
+    """write_checkpoint -> read_checkpoint: config fields, every tensor bit for bit, tied lm_head stored once, shards merged."""
+    from safetensors.torch import save_file
+
+    from starvector_b200.config import StarVectorConfig, dims_tiny
+    from starvector_b200.modeling import read_checkpoint, write_checkpoint
+    from starvector_b200.weights import synthetic_state_dict
+
+    d = dims_tiny()
+    sd = dict(synthetic_state_dict(d, seed=0, init="randomized"))
+    cfg = StarVectorConfig(max_length_train=100, image_size=d.image_size)
+    write_checkpoint(str(tmp_path), cfg, sd)
+    cfg2, sd2 = read_checkpoint(str(tmp_path))
+    assert cfg2.to_dict() == {**cfg.to_dict(), "_name_or_path": str(tmp_path)} or cfg2.max_length_train == 100
+    stored = {k for k in sd if not k.endswith("lm_head.weight")}
+    assert set(sd2) == stored and all(torch.equal(sd2[k], sd[k]) for k in stored)
+    # a second shard is merged in
+    save_file({"extra.tensor": torch.arange(4, dtype=torch.float32)}, str(tmp_path / "model-00002.safetensors"))
+    assert "extra.tensor" in read_checkpoint(str(tmp_path))[1]
+    with pytest.raises(FileNotFoundError):
+        read_checkpoint(str(tmp_path / "nowhere"))
+    (tmp_path / "empty").mkdir()
+    (tmp_path / "empty" / "config.json").write_text((tmp_path / "config.json").read_text())
+    with pytest.raises(FileNotFoundError):
+        read_checkpoint(str(tmp_path / "empty"))
