@@ -25,8 +25,13 @@ def main():
         cases.append({"hwc": hwc, "seed": seed, "alpha": alpha, "image": torch.from_numpy(a),
                       "resized_u8": torch.from_numpy(P.reference_resized_u8(a, 224, alpha)),      # right after Image.resize
                       "sha256_f32": P.tensor_sha256(ref), "sha256_bf16": P.tensor_sha256(ref.to(torch.bfloat16))})
+    siglip = []
+    for hwc, seed in [((50, 70, 4), 7), ((400, 300, 3), 8)]:
+        a = P.synthetic_image(*hwc, seed=seed)
+        ref = P.reference_siglip_transform(a, 384)
+        siglip.append({"hwc": hwc, "seed": seed, "sha256_f32": P.tensor_sha256(ref), "sha256_bf16": P.tensor_sha256(ref.to(torch.bfloat16))})
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "preprocess_v1.pt")
-    torch.save({"cases": cases, "versions": {"pillow": PIL.__version__, "torchvision": torchvision.__version__, "torch": torch.__version__}}, out)
+    torch.save({"cases": cases, "siglip_cases": siglip, "versions": {"pillow": PIL.__version__, "torchvision": torchvision.__version__, "torch": torch.__version__}}, out)
     print(out, os.path.getsize(out))
 
 

@@ -68,6 +68,28 @@ def reference_transform(arr: np.ndarray, size: int = 224, alpha: int = ALPHA_WHI
     return transforms.Normalize(mean=mean, std=std)(transforms.ToTensor()(img))
 
 
+def reference_siglip_transform(arr: np.ndarray, size: int = 384) -> torch.Tensor:
+    """float32 [3,size,size] from the PIL-based SigLIP image processor of the installed transformers
+    (`SiglipImageProcessorPil`: convert RGB, PIL bicubic resize to (size,size), x/255, mean = std = 0.5) — what
+    `AutoProcessor.from_pretrained("google/siglip-*")` gave under the reference's pinned transformers 4.49
+    (reference image_encoder.py:32-48, called at :119)."""
+    import warnings
+
+    from transformers.models.siglip import SiglipImageProcessorPil
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        proc = SiglipImageProcessorPil(size={"height": size, "width": size})
+    return proc(images=_to_pil(arr), return_tensors="pt").pixel_values[0]
+
+
+def restated_siglip_transform(arr: np.ndarray, size: int = 384) -> torch.Tensor:
+    """numpy restatement of the above: alpha dropped, direct (w,h)->(size,size) resample, table normalisation."""
+    u8 = resize_bicubic_u8(np.ascontiguousarray(arr[..., :3]), size, size)
+    lut = normalize_lut((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
+    return torch.from_numpy(np.stack([lut[c][u8[..., c]] for c in range(3)]))
+
+
 def reference_resized_u8(arr: np.ndarray, size: int = 224, alpha: int = ALPHA_WHITE) -> np.ndarray:
     """uint8 [size,size,3] right after the PIL resize (before ToTensor/Normalize)."""
     x = reference_transform(arr, size, alpha, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0))

@@ -59,6 +59,15 @@ def test_golden_fixture(golden_dir):
         assert P.tensor_sha256(got.to(torch.bfloat16)) == case["sha256_bf16"]
 
 
+def test_siglip_restatement_and_golden(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "preprocess_v1.pt"), weights_only=False)
+    for case in g["siglip_cases"]:
+        a = P.synthetic_image(*case["hwc"], seed=case["seed"])
+        ref, got = P.reference_siglip_transform(a, 384), P.restated_siglip_transform(a, 384)
+        assert torch.equal(ref, got)
+        assert P.tensor_sha256(got) == case["sha256_f32"] and P.tensor_sha256(got.to(torch.bfloat16)) == case["sha256_bf16"]
+
+
 def test_library_taps_and_table_equal_oracle():
     lib = _lib.load()
     for out in (224, 384):
