@@ -1,12 +1,16 @@
 """Widening rows of SURVEY.md §8f-4 on the GPU: token streaming (`sv_generate_stream`, the facade's `streamer=` kwarg the
 reference's serving worker passes), `num_return_sequences` (`generate_im2svg_grpo`), batches above `max_batch`.  These are
 self-consistency tests of host-side control flow around kernels whose parity the other GPU test files establish."""
+import os
+
 import pytest
 import torch
 
+from oracle import preprocess as PRE
 from starvector_b200.config import dims_tiny
 from starvector_b200.engine import Engine, GenerationParams
 from starvector_b200.modeling import StarVectorForCausalLM
+from starvector_b200.preprocess import SiglipImageProcessor
 from starvector_b200.weights import synthetic_images, synthetic_state_dict
 
 pytestmark = pytest.mark.gpu
@@ -141,3 +145,12 @@ def test_streamer_kwarg_streams_tokens(model):
     assert "".join(pieces) == tok.decode(ids[0, P:].tolist(), skip_special_tokens=True) and len(result["text"]) == 1
     with pytest.raises(ValueError):
         m.model.generate_im2svg({"image": img}, streamer=Collect(), num_beams=2, max_length=kw["max_length"])
+
+
+def test_siglip_golden_fixture(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "preprocess_v1.pt"), weights_only=False)
+    proc = SiglipImageProcessor(size=384)
+    for case in g["siglip_cases"]:
+        a = PRE.synthetic_image(*case["hwc"], seed=case["seed"])
+        got = proc(images=a).pixel_values[0].cpu()
+        assert PRE.tensor_sha256(got) == case["sha256_f32"] and PRE.tensor_sha256(got.to(torch.bfloat16)) == case["sha256_bf16"]
