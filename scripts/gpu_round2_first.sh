@@ -1,6 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: everything that was built after round 1's GPU budget ran out gets measured or
 # checked in one go (about 6-8 minutes).  Output lands in gpurun_out/r02_*.
+#   python -m starvector_b200.build --variant nwc4      # here, before the call: the .so travels with the snapshot
 #   gpurun --timeout 900 -- 'bash scripts/gpu_round2_first.sh'
 set -u
 cd "$(dirname "$0")/.."
@@ -17,6 +18,12 @@ TAILN=22 run timeline_ctx2300 python scripts/timeline_decode.py --ctx 2048 --new
 for mode in 0 1 2; do
   SV_MEGA=$mode TAILN=1 run bench_mega$mode python bench.py --steps 2 --warmup 3 --max-new-tokens 512 --no-cpu-baseline
 done
+NWC4=starvector_b200/libstarvector_b200_nwc4.so
+if [ -f $NWC4 ]; then
+  SV_LIB_PATH=$NWC4 run nwc4_parity python -m pytest tests/test_engine_gpu.py tests/test_full_1b_gpu.py -q --tb=short -m gpu
+  SV_LIB_PATH=$NWC4 TAILN=1 run bench_nwc4 python bench.py --steps 2 --warmup 3 --max-new-tokens 512 --no-cpu-baseline
+  SV_LIB_PATH=$NWC4 TAILN=22 run timeline_nwc4 python scripts/timeline_decode.py --ctx 32 --new 24 --json gpurun_out/r02_timeline_nwc4.json
+fi
 # 4. beam search with and without the step graph; preprocessing after the two layout changes
 TAILN=1 run beam_eager python scripts/beam_bench.py --num-beams 2 --max-new-tokens 512
 SV_STEP_GRAPH=1 TAILN=1 run beam_graph python scripts/beam_bench.py --num-beams 2 --max-new-tokens 512

@@ -2,6 +2,7 @@
 
     python -m starvector_b200.build            # incremental
     python -m starvector_b200.build --force
+    python -m starvector_b200.build --variant nwc4     # experimental second library, see VARIANTS
 
 The library has a plain C ABI (include/starvector_b200.h) and links only the static CUDA
 runtime, so it travels to the GPU box with the repo snapshot and loads through ctypes.
@@ -40,7 +41,20 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+# Experimental builds of the same sources (run-time selection: SV_LIB_PATH=<that .so>); never loaded by default.
+VARIANTS = {
+    # 4 consumer warps + producer per GEMV CTA, 3 ring slots, two CTAs per SM
+    "nwc4": ["-DSV_NWC=4", "-DSV_STAGES=3", "-DSV_MINBLOCKS=2"],
+}
+
+
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    global OBJ, LIB
+    extra = []
+    if variant:
+        extra = VARIANTS[variant]
+        OBJ = os.path.join(HERE, f"build_{variant}")
+        LIB = os.path.join(HERE, f"libstarvector_b200_{variant}.so")
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
@@ -49,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + hdrs):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", s, "-o", o])
+            jobs.append([nvcc, *NVCC_FLAGS, *extra, "-c", s, "-o", o])
 
     def run(cmd):
         if verbose:
@@ -67,4 +81,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose=True, variant=_variant))

@@ -34,12 +34,28 @@
 namespace sv {
 namespace mega {
 
-constexpr int NWC = 8;                               // consumer warps
+// Build-time shape of a GEMV CTA.  The shipped library uses the defaults (8 consumer warps, 5 ring slots, one CTA per
+// SM).  `python -m starvector_b200.build --variant nwc4` builds a second library (selected at run time with SV_LIB_PATH)
+// with 4 consumer warps, 3 slots and TWO CTAs per SM, so that under PDL the next kernel's CTAs are already resident —
+// and their producer warps already streaming — while the previous kernel drains (DESIGN.md §7c experiment (c)).
+#ifndef SV_NWC
+#define SV_NWC 8
+#endif
+#ifndef SV_STAGES
+#define SV_STAGES 5
+#endif
+#ifndef SV_MINBLOCKS
+#define SV_MINBLOCKS 1
+#endif
+constexpr int NWC = SV_NWC;                          // consumer warps
+static_assert(NWC == 8 || NWC == 4, "the 128-thread tile epilogue needs >= 4 consumer warps; chunking assumes 32 % NWC == 0");
 constexpr int NCT = NWC * 32;                        // consumer threads
 constexpr int NTHREADS = NCT + 32;                   // + producer warp
 constexpr int KS_MAX = 1024;                         // k elements per ring slot row
+constexpr int CPW = KS_MAX / 32 / NWC;               // 32-wide k chunks per consumer warp and slot (4 with 8 warps)
 constexpr int SLOT_BYTES = 16 * (KS_MAX * 2 + 64);   // 16 rows x (2 KB + 64 B pad)
-constexpr int STAGES = 5;
+constexpr int STAGES = SV_STAGES;
+constexpr int RING_MINBLOCKS = SV_MINBLOCKS;         // gemv_ring_kernel CTAs per SM
 constexpr int D = 128;
 constexpr int PSZ = 32 + 16 * D;                     // floats per attention partial: m[16] l[16] acc[16][D]
 constexpr int ATT_BYTES = 4 * PSZ * 4;               // tree-merge buffer: 4 warp partials
@@ -190,29 +206,29 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
   const Plan p = make_plan(N, K, cx.cta, cx.ncta);
   const int warp = cx.warp, g = cx.g, t = cx.t;
   const int cps = p.KS >> 5;                         // 32-wide chunks per slot row
-  const int cpws = (cps + NWC - 1) / NWC;            // chunks per warp per slot (<= 4)
+  const int cpws = (cps + NWC - 1) / NWC;            // chunks per warp per slot (<= CPW)
   const bool row_ok = g < a.B;
   const bf16* xp = X + (int64_t)(row_ok ? g : 0) * K + 8 * t;
   const bool big_k = p.nstg > 2;
 
   // activations for the whole phase live in registers when K <= 2048 (8 fragments per lane)
-  uint4 xr[8];
+  uint4 xr[2 * CPW];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) xr[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = 0; i < 2 * CPW; ++i) xr[i] = make_uint4(0u, 0u, 0u, 0u);
   if (!big_k && p.ntile > 0) {
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < CPW; ++j) {
         const int cl = warp + NWC * j;
         const bool okc = ks < p.nstg && j < cpws && cl < cps;
-        if (okc && row_ok) xr[ks * 4 + j] = ldcg16(xp + (ks * cps + cl) * 32);
+        if (okc && row_ok) xr[ks * CPW + j] = ldcg16(xp + (ks * cps + cl) * 32);
       }
     }
     if constexpr (HAS_LN) {
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 2 * CPW; ++i) {
         float f[8];
         unpack8(xr[i], f);
 #pragma unroll
@@ -229,11 +245,11 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CPW; ++j) {
           const bool okc = ks < p.nstg && j < cpws && (warp + NWC * j) < cps;
           if (okc) {
             float f[8];
-            unpack8(xr[ks * 4 + j], f);
+            unpack8(xr[ks * CPW + j], f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) { const float dlt = f[e] - mean; q += dlt * dlt; }
           }
@@ -251,17 +267,17 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CPW; ++j) {
           const int cl = warp + NWC * j;
           const bool okc = ks < p.nstg && j < cpws && cl < cps;
           float f[8], wf[8], bfv[8];
-          unpack8(xr[ks * 4 + j], f);
+          unpack8(xr[ks * CPW + j], f);
           const int ch = okc ? ks * cps + cl : 0;
           unpack8(ldg_cached(ln_w + ch * 32 + 8 * t), wf);
           unpack8(ldg_cached(ln_b + ch * 32 + 8 * t), bfv);
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = (row_ok && okc) ? (f[e] - mean) * rstd * wf[e] + bfv[e] : 0.f;
-          xr[ks * 4 + j] = pack8(f);       // ln output is a bf16 tensor in the reference; 0 on padded chunks
+          xr[ks * CPW + j] = pack8(f);       // ln output is a bf16 tensor in the reference; 0 on padded chunks
         }
       }
     }
@@ -275,7 +291,7 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
       float sv = 0.f;
       for (int ks = 0; ks < p.nstg; ++ks) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CPW; ++j) {
           const int cl = warp + NWC * j;
           if (row_ok && j < cpws && cl < cps) {
             float f[8];
@@ -294,7 +310,7 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
       float q = 0.f;
       for (int ks = 0; ks < p.nstg; ++ks) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CPW; ++j) {
           const int cl = warp + NWC * j;
           if (row_ok && j < cpws && cl < cps) {
             float f[8];
@@ -325,11 +341,11 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
           mbar_wait(r.full0 + 8u * r.slot, r.phase);
           const uint32_t sb = r.base + r.slot * SLOT_BYTES + g * p.pitch + t * 16;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < CPW; ++j) {
             const int cl = warp + NWC * j;
             if (j < cpws && cl < cps) {
               const uint4 lo = lds16(sb + cl * 64), hi = lds16(sb + 8 * p.pitch + cl * 64);
-              const uint4 xv = xr[ks * 4 + j];
+              const uint4 xv = xr[ks * CPW + j];
               mma_bf16_16816(c, lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
               mma_bf16_16816(c, lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
             }
@@ -343,10 +359,10 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
       // K > 2048: activation fragments are fetched per slab from L2, one slab ahead of their use (with HAS_LN the
       // LayerNorm affine of the same columns rides along and the fragment is normalised after the slab's MMAs).
       constexpr bool LNB = HAS_LN && LN_BIGK;
-      uint4 xc[4], xn[4], wn[LNB ? 4 : 1], bn[LNB ? 4 : 1];
+      uint4 xc[CPW], xn[CPW], wn[LNB ? CPW : 1], bn[LNB ? CPW : 1];
       auto fetch = [&](int ks) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CPW; ++j) {
           const int cl = warp + NWC * j;
           const bool okc = ks < p.nstg && j < cpws && cl < cps;
           const int ch = okc ? ks * cps + cl : 0;
@@ -359,7 +375,7 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
       };
       auto promote = [&](int ks) {             // xn (raw) -> xc (what the MMAs consume)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CPW; ++j) {
           if constexpr (LNB) {
             const bool okc = ks < p.nstg && j < cpws && (warp + NWC * j) < cps;
             float f[8], wf[8], bfv[8];
@@ -379,7 +395,7 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
         mbar_wait(r.full0 + 8u * r.slot, r.phase);
         const uint32_t sb = r.base + r.slot * SLOT_BYTES + g * p.pitch + t * 16;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CPW; ++j) {
           const int cl = warp + NWC * j;
           if (j < cpws && cl < cps) {
             const uint4 lo = lds16(sb + cl * 64), hi = lds16(sb + 8 * p.pitch + cl * 64);
@@ -787,7 +803,7 @@ SV_DEVINL constexpr int ring_smem_bytes(int nslots) { return nslots * SLOT_BYTES
 
 // (A 2-CTA/SM register budget (96 regs) so that consecutive kernels co-reside under PDL was measured 25% slower.)
 template <bool HAS_LN, int EPI, bool LN_BIGK = false>
-__global__ void __launch_bounds__(NTHREADS, 1) gemv_ring_kernel(const RingGemvArgs ra) {
+__global__ void __launch_bounds__(NTHREADS, RING_MINBLOCKS) gemv_ring_kernel(const RingGemvArgs ra) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -854,7 +870,7 @@ bool decode_mega_realloc_supported() { return g_mega_realloc_ok; }
 int decode_mega_ncta() { return g_mega_ncta; }
 bool decode_mega_supported(int H, int I, int head_dim, int max_batch) {
   auto okk = [](int K) { return K % 32 == 0 && (K <= mega::KS_MAX ? true : K % mega::KS_MAX == 0); };
-  return g_mega_ncta > 0 && head_dim == mega::D && okk(H) && okk(I) && H <= 2 * mega::KS_MAX && max_batch <= 8;
+  return mega::NWC == 8 && g_mega_ncta > 0 && head_dim == mega::D && okk(H) && okk(I) && H <= 2 * mega::KS_MAX && max_batch <= 8;
 }
 
 cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st) {
@@ -912,10 +928,15 @@ cudaError_t gemv_ring_init() {   // set the shared-memory opt-in outside of any 
 
 bool gemv_ring_supported(int K, bool has_ln) { (void)has_ln; return K >= 32 && K % 32 == 0; }
 
-int gemv_ring_ntiles(int N) {
+static int ring_ncta() {                  // CTAs of one ring GEMV: every SM, RING_MINBLOCKS each
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  return nsm * mega::RING_MINBLOCKS;
+}
+
+int gemv_ring_ntiles(int N) {
+  const int nsm = ring_ncta();
   const int rows_per_cta = (N + nsm - 1) / nsm, tpc = (rows_per_cta + 15) / 16, R = (rows_per_cta + tpc - 1) / tpc;
   return (N + R - 1) / R;
 }
@@ -928,12 +949,10 @@ void launch_gemv_ring(const RingGemvLaunch& g, cudaStream_t st) {
   ra.X = g.X; ra.W = g.W; ra.bias = g.bias; ra.res = g.res; ra.ln_w = g.ln_w; ra.ln_b = g.ln_b; ra.Y = g.Y;
   ra.N = g.N; ra.K = g.K; ra.act = g.act;
   ra.next_w = g.next_w; ra.next_bytes = g.next_bytes;
-  int dev = 0, nsm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int nsm = ring_ncta();
   {   // ring depth: what this CTA will stream, capped so the next kernel's CTA can co-reside (227 KB per SM)
     static int cap = 0;
-    if (cap == 0) { const char* c = getenv("SV_RING_SLOTS"); cap = c ? atoi(c) : 5; if (cap < 1 || cap > 6) cap = 5; }
+    if (cap == 0) { const char* c = getenv("SV_RING_SLOTS"); cap = c ? atoi(c) : mega::STAGES; if (cap < 1 || cap > 6) cap = mega::STAGES; }
     const int rows_per_cta = (g.N + nsm - 1) / nsm, tpc = (rows_per_cta + 15) / 16;
     int ks = 32;
     for (int c : {1024, 768, 512, 256, 128, 64}) if (c <= g.K && g.K % c == 0) { ks = c; break; }
