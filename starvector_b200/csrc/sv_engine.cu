@@ -312,7 +312,8 @@ bool build_buffers(sv_engine* e) {
   AL(d_x, B * H); AL(d_ln, B * H); AL(d_qkv, B * e->qkv_cols); AL(d_attn, B * H); AL(d_h, B * I); AL(d_last, B * H);
   AL(logits, B * d.vocab); AL(logits_f32, B * d.vocab);
   AL(attn_partial, B * d.n_kv_head * kMaxSplit * (32 + 16 * D));
-  AL(amax_val, (int64_t)gemv_ntiles(d.vocab) * 8); AL(amax_idx, (int64_t)gemv_ntiles(d.vocab) * 8);
+  const int64_t amax_rows = std::max(gemv_ntiles(d.vocab), gemv_ring_ntiles(d.vocab));   // either lm_head kernel's tile count
+  AL(amax_val, amax_rows * 8); AL(amax_idx, amax_rows * 8);
   AL(attn_counters, B * d.n_kv_head);
   AL(mega_layers, d.n_layer); AL(mega_barrier, 4); AL(mega_dbg, 1024);
   e->cache_layer_stride = B * d.n_kv_head * (int64_t)e->tcap * D;
@@ -900,7 +901,7 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
   // HF stop rules and embeds the token for the first decode step.
   const bool fused = e->fused_decode;
   const bool fused_select = fused && !p->do_sample;
-  const int ntiles = gemv_ntiles(e->d.vocab);
+  const int ntiles = e->use_ring ? gemv_ring_ntiles(e->d.vocab) : gemv_ntiles(e->d.vocab);   // equal in the default build
   auto select_step = [&](int advance_len, bool have_partials, bool pdl) {
     if (fused_select) {
       launch_select_fused(e->logits, e->d.vocab, B, have_partials ? e->amax_val : nullptr, e->amax_idx, ntiles, e->state,
