@@ -928,11 +928,14 @@ cudaError_t gemv_ring_init() {   // set the shared-memory opt-in outside of any 
 
 bool gemv_ring_supported(int K, bool has_ln) { (void)has_ln; return K >= 32 && K % 32 == 0; }
 
-static int ring_ncta() {                  // CTAs of one ring GEMV: every SM, RING_MINBLOCKS each
+// CTAs of one ring GEMV: one per SM in every build.  With RING_MINBLOCKS = 2 the CTA is small enough for two per SM, and
+// the second slot is deliberately left free: it is where the NEXT kernel's CTA (launched early through PDL) becomes
+// resident and starts filling its ring while this kernel is still computing.
+static int ring_ncta() {
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  return nsm * mega::RING_MINBLOCKS;
+  return nsm;
 }
 
 int gemv_ring_ntiles(int N) {
