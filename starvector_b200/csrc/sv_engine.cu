@@ -83,6 +83,13 @@ struct sv_engine {
   unsigned int* mega_barrier = nullptr;
   long long* mega_dbg = nullptr;
   bool mega_debug = false;
+  // dataflow persistent decode kernel (sv_decode_flow.cu): flagged exchange buffers in one allocation
+  bool use_flow = false, flow_realloc = false;
+  uint8_t* flow_mem = nullptr;
+  size_t flow_bytes = 0;
+  uint32_t *f_xa = nullptr, *f_xb = nullptr, *f_qkv = nullptr, *f_att = nullptr, *f_hb = nullptr;
+  unsigned long long *f_part = nullptr, *f_amax = nullptr;
+  int flow_epoch = 0;               // phase-tag epoch: steps run through the flow kernel since the buffers were cleared
   bf16 *kscratch = nullptr, *vscratch = nullptr;   // one layer of cache, for beam-search reorders
   bf16 *kcache, *vtcache;           // [layer][max_batch][n_kv][tcap][D] / [layer][max_batch][n_kv][D][tcap]
   int64_t cache_layer_stride = 0;
@@ -316,6 +323,25 @@ bool build_buffers(sv_engine* e) {
   AL(amax_val, amax_rows * 8); AL(amax_idx, amax_rows * 8);
   AL(attn_counters, B * d.n_kv_head);
   AL(mega_layers, d.n_layer); AL(mega_barrier, 4); AL(mega_dbg, 1024);
+  {
+    // flagged exchange buffers of the dataflow decode kernel, cleared together when a sequence starts
+    const size_t n_x = (size_t)B * H * 4, n_qkv = (size_t)B * e->qkv_cols * 4, n_hb = (size_t)B * I * 4;
+    const size_t n_part = (size_t)B * d.n_kv_head * decode_flow_max_splits() * decode_flow_partial_floats() * 8;
+    const size_t n_amax = (size_t)gemv_ring_ntiles(d.vocab) * 8 * 8;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    e->flow_bytes = 3 * up(n_x) + up(n_qkv) + up(n_hb) + up(n_part) + up(n_amax);
+    AL(flow_mem, (int64_t)e->flow_bytes);
+    if (ok) {
+      uint8_t* q = e->flow_mem;
+      e->f_xa = reinterpret_cast<uint32_t*>(q); q += up(n_x);
+      e->f_xb = reinterpret_cast<uint32_t*>(q); q += up(n_x);
+      e->f_att = reinterpret_cast<uint32_t*>(q); q += up(n_x);
+      e->f_qkv = reinterpret_cast<uint32_t*>(q); q += up(n_qkv);
+      e->f_hb = reinterpret_cast<uint32_t*>(q); q += up(n_hb);
+      e->f_part = reinterpret_cast<unsigned long long*>(q); q += up(n_part);
+      e->f_amax = reinterpret_cast<unsigned long long*>(q);
+    }
+  }
   e->cache_layer_stride = B * d.n_kv_head * (int64_t)e->tcap * D;
   AL(kcache, e->cache_layer_stride * d.n_layer); AL(vtcache, e->cache_layer_stride * d.n_layer);
   AL(kscratch, e->cache_layer_stride); AL(vscratch, e->cache_layer_stride);
@@ -327,6 +353,7 @@ bool build_buffers(sv_engine* e) {
   cudaMemset(e->kcache, 0, (size_t)e->cache_layer_stride * d.n_layer * sizeof(bf16));
   cudaMemset(e->vtcache, 0, (size_t)e->cache_layer_stride * d.n_layer * sizeof(bf16));
   cudaMemset(e->state, 0, sizeof(GenState));
+  cudaMemset(e->flow_mem, 0, e->flow_bytes);
   cudaMemset(e->attn_counters, 0, (size_t)B * d.n_kv_head * sizeof(int));
   return cudaMallocHost(reinterpret_cast<void**>(&e->host_flag), 64) == cudaSuccess;
 }
@@ -525,6 +552,19 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
   return SV_OK;
 }
 
+FlowLaunch flow_launch_desc(sv_engine* e, int B) {
+  FlowLaunch m{};
+  m.layers_dev = e->mega_layers; m.n_layer = e->d.n_layer; m.B = B; m.H = e->d.hidden; m.I = e->d.n_inner;
+  m.n_head = e->d.n_head; m.n_kv = e->d.n_kv_head; m.qkv_cols = e->qkv_cols; m.vocab = e->d.vocab; m.tcap = e->tcap;
+  m.n_positions = e->d.n_positions; m.ln_eps = e->d.ln_eps; m.wte = e->wte; m.wpe = e->wpe; m.lnf_w = e->lnf_w;
+  m.lnf_b = e->lnf_b; m.lm_head = e->lm_head; m.x_plain = e->d_x; m.logits = e->logits;
+  m.xa = e->f_xa; m.xb = e->f_xb; m.qkv = e->f_qkv; m.att = e->f_att; m.hb = e->f_hb; m.part = e->f_part; m.amax = e->f_amax;
+  m.state = e->state; m.params = e->params; m.seen = e->seen; m.next_ids = e->next_ids; m.out_ids = e->out_ids;
+  m.dbg = e->mega_debug ? e->mega_dbg : nullptr;
+  m.realloc = e->flow_realloc;
+  return m;
+}
+
 int nsplit_for(const sv_engine* e, int total_len) {
   int blocks = (total_len + 31) / 32;
   return std::max(1, std::min(kMaxSplit, blocks));
@@ -554,6 +594,10 @@ static int finish_prefill_impl(sv_engine* e, int batch, int prefix_len, float* l
   hs.cur_len = e->prefix_len;
   for (int b = 0; b < batch; ++b) hs.unfinished[b] = 1;
   SV_CK(e, cudaMemcpyAsync(e->state, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));   // pageable: staged synchronously
+  if (e->use_flow) {                 // new sequence: no word of the exchange buffers may carry a tag of the coming epochs
+    SV_CK(e, cudaMemsetAsync(e->flow_mem, 0, e->flow_bytes, st));
+    e->flow_epoch = 0;
+  }
   if (last_logits) launch_logits_to_float(e->logits, last_logits, (int64_t)batch * e->d.vocab, st);
   SV_CK(e, cudaGetLastError());
   e->prefilled = true;
@@ -629,6 +673,9 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   e->use_mega = mg && (!strcmp(mg, "1") || !strcmp(mg, "2"));   // (opt-in until it beats the graph path: DESIGN.md "decode modes")
   e->mega_realloc = mg && !strcmp(mg, "2");       // "2" = the same kernel with setmaxnreg register reallocation
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
+  { const char* fl = getenv("SV_FLOW");          // dataflow persistent kernel: default for greedy decode; "0" = per-phase graph
+    e->use_flow = !(fl && !strcmp(fl, "0")) && !e->use_mega;
+    e->flow_realloc = fl && !strcmp(fl, "2"); }  // "2" = three warpgroups + setmaxnreg
   { const char* sg = getenv("SV_STEP_GRAPH"); e->step_graph = sg && !strcmp(sg, "1"); }
   const char* at = getenv("SV_ATTN");             // "ticket" = global-scratch + atomic-ticket merge instead of the cluster/DSMEM merge
   if (at && !strcmp(at, "ticket")) e->use_cluster_attn = false;
@@ -664,12 +711,14 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
                         L.fc2_w, L.fc2_b, e->kcache + e->cache_layer_stride * i, e->vtcache + e->cache_layer_stride * i};
     }
     if (cudaMemcpy(e->mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
-        decode_mega_init() != cudaSuccess || gemv_ring_init() != cudaSuccess) {
+        decode_mega_init() != cudaSuccess || decode_flow_init() != cudaSuccess || gemv_ring_init() != cudaSuccess) {
       sv_engine_destroy(e);
       return fail(nullptr, SV_ERR_CUDA, "persistent decode kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (!decode_mega_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch) || !e->fused_decode) e->use_mega = false;
     if (e->mega_realloc && !decode_mega_realloc_supported()) e->mega_realloc = false;
+    if (!decode_flow_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch, e->window, e->v2) || !e->fused_decode) e->use_flow = false;
+    if (e->flow_realloc && !decode_flow_realloc_supported()) e->flow_realloc = false;
   }
   if (attention_decode_fused_init() != cudaSuccess || attention_decode_cluster_init() != cudaSuccess) {
     sv_engine_destroy(e);
@@ -853,6 +902,16 @@ int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream
     }
     SV_CK(e, cudaGraphLaunch(ge.exec, st));
     e->launches += ge.kernels;
+  } else if (e->use_flow) {
+    // one token through the dataflow kernel: embed (plain) -> all layers -> logits, no selection
+    const sv_model_desc& d = e->d;
+    launch_embed_tokens(ids, e->wte, e->wpe, e->state, e->d_x, e->cur_batch, d.hidden, d.vocab, d.n_positions, st);
+    FlowLaunch m = flow_launch_desc(e, e->cur_batch);
+    m.nsteps = 1; m.step0 = e->flow_epoch; m.cur_len0 = e->host_cur_len; m.first_plain = 1; m.do_select = 0;
+    cudaError_t ce = launch_decode_flow(m, st);
+    if (ce != cudaSuccess) return fail(e, SV_ERR_CUDA, "dataflow decode launch failed: %s", cudaGetErrorString(ce));
+    e->flow_epoch += 1;
+    launch_advance_len(e->state, st);
   } else {
     r = e->fused_decode
             ? run_decode_layers_fused(e, ids, e->cur_batch, attention_decode_fused_ncta(e->host_cur_len + 1), e->use_pdl, st)
@@ -917,7 +976,8 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
   const int nsplit = fused ? attention_decode_fused_ncta(e->prefix_len + max_new) : nsplit_for(e, e->prefix_len + max_new);
   const long long key = (long long)B * 100000 + nsplit * 8 + (p->do_sample ? 1 : 0) + (fused ? 2 : 0) + (e->use_pdl ? 4 : 0);
   GraphEntry& ge = e->graphs[key];
-  if (!ge.exec && max_new > 1 && !(e->use_mega && fused_select)) {
+  const bool flow = e->use_flow && fused_select;
+  if (!ge.exec && max_new > 1 && !(e->use_mega && fused_select) && !flow) {
     for (int attempt = 0; attempt < 2 && !ge.exec; ++attempt) {
       const bool pdl = e->use_pdl && fused && attempt == 0;
       int64_t counted = 0;
@@ -946,7 +1006,7 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
 
   const int poll = p->poll_interval > 0 ? p->poll_interval : 16;
   const bool can_stop = p->eos_token_id >= 0 || p->n_stop_ids > 0;
-  const bool mega = e->use_mega && fused_select;
+  const bool mega = e->use_mega && fused_select && !flow;
   // streaming: at every poll, tokens [emitted, step) of every row go to the callback through a pinned staging buffer
   int emitted = 0;
   bool cancelled = false;
@@ -973,6 +1033,34 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
   SV_CK(e, cudaEventRecord(e->ev_t0, st));
   int steps = 0;
   bool done = false;
+  if (flow) {
+    // dataflow persistent kernel: up to `chunk` whole tokens per cooperative launch, no host work in between
+    const int chunk = (can_stop || cb) ? poll : 512;
+    FlowLaunch m = flow_launch_desc(e, B);
+    m.do_select = 1;
+    if (e->mega_debug) cudaMemsetAsync(e->mega_dbg, 0, 1024 * sizeof(long long), st);
+    int left = max_new - 1;
+    bool first = true;
+    while (left > 0 && !done) {
+      m.nsteps = std::min(left, chunk);
+      m.step0 = e->flow_epoch; m.cur_len0 = e->prefix_len + steps; m.first_plain = first ? 1 : 0;
+      cudaError_t ce = launch_decode_flow(m, st);
+      if (ce != cudaSuccess) return fail(e, SV_ERR_CUDA, "dataflow decode launch failed: %s", cudaGetErrorString(ce));
+      first = false;
+      m.dbg = nullptr;
+      e->flow_epoch += m.nsteps;
+      left -= m.nsteps;
+      steps += m.nsteps;
+      if (cb && left > 0) {
+        const int r = poll_device(done);
+        if (r != SV_OK) return r;
+      } else if (can_stop && left > 0) {
+        SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->done, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SV_CK(e, cudaStreamSynchronize(st));
+        done = e->host_flag[0] != 0;
+      }
+    }
+  }
   if (mega) {
     // persistent kernel: up to `chunk` whole tokens per cooperative launch, no host work in between
     const int chunk = (can_stop || cb) ? poll : 256;
@@ -1004,7 +1092,7 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
       }
     }
   }
-  for (int s = 1; s < max_new && !done && !mega; ++s) {
+  for (int s = 1; s < max_new && !done && !mega && !flow; ++s) {
     SV_CK(e, cudaGraphLaunch(ge.exec, st));
     e->launches += ge.kernels;
     ++steps;
@@ -1112,7 +1200,7 @@ const char* sv_engine_describe(sv_engine* e) {
   if (!e) return "";
   char buf[512];
   snprintf(buf, sizeof(buf), "decode=%s attn=%s pdl=%d l2pf=%d linear_impl=%d mega[%s]",
-           !e->fused_decode ? "legacy-kernels" : (e->use_mega ? (e->mega_realloc ? "persistent-kernel-setmaxnreg" : "persistent-kernel") : (e->use_ring ? "ring-gemv-graph" : "reg-gemv-graph")),
+           !e->fused_decode ? "legacy-kernels" : e->use_flow ? (e->flow_realloc ? "dataflow-kernel-setmaxnreg" : "dataflow-kernel") : (e->use_mega ? (e->mega_realloc ? "persistent-kernel-setmaxnreg" : "persistent-kernel") : (e->use_ring ? "ring-gemv-graph" : "reg-gemv-graph")),
            e->use_cluster_attn ? "cluster-dsmem" : "ticket", (int)e->use_pdl, (int)e->use_l2_prefetch, e->linear_impl, decode_mega_status());
   e->describe = buf;
   return e->describe.c_str();

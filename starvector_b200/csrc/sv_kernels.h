@@ -166,4 +166,34 @@ bool decode_mega_supported(int H, int I, int head_dim, int max_batch);
 bool decode_mega_realloc_supported();
 cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st);
 
+// ---- sv_decode_flow.cu : dataflow persistent decode kernel (flagged activation words through L2, no grid barriers)
+struct FlowLaunch {
+  const MegaLayer* layers_dev;
+  int n_layer, B, H, I, n_head, n_kv, qkv_cols, vocab, tcap, n_positions;
+  float ln_eps;
+  const bf16 *wte, *wpe, *lnf_w, *lnf_b, *lm_head;
+  bf16 *x_plain, *logits;
+  uint32_t *xa, *xb, *qkv, *att, *hb;          // flagged bf16 words
+  unsigned long long *part, *amax;             // flagged fp32 words / argmax partials
+  GenState* state;
+  const GenParamsDev* params;
+  uint8_t* seen;
+  int32_t *next_ids, *out_ids;
+  int nsteps;          // tokens in this launch
+  int step0;           // phase-tag epoch of the first step (monotonic since the exchange buffers were cleared)
+  int cur_len0;        // tokens in the KV cache when the launch starts
+  int first_plain;     // 1: the first step's input is x_plain (plain bf16) and gets converted to flagged words
+  int do_select;       // 1: greedy select + embed after every step; 0: stop after the logits (teacher forcing)
+  long long* dbg;
+  bool realloc;
+};
+cudaError_t decode_flow_init();
+int decode_flow_ncta();
+int decode_flow_max_splits();
+int decode_flow_partial_floats();
+const char* decode_flow_status();
+bool decode_flow_supported(int H, int I, int head_dim, int max_batch, int window, bool rope);
+bool decode_flow_realloc_supported();
+cudaError_t launch_decode_flow(const FlowLaunch& m, cudaStream_t st);
+
 }  // namespace sv
