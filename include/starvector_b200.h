@@ -164,8 +164,9 @@ SV_API int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_
 SV_API int64_t sv_launch_count(const sv_engine* e);
 /* Human-readable configuration of the engine (decode mode, PDL, kernel selection) for logs/bench JSON. */
 SV_API const char* sv_engine_describe(sv_engine* e);
-/* Debug (SV_MEGA_DEBUG=1): SM-clock stamps CTA 0 took around every grid barrier of the first token of the
- * last persistent-decode launch; n <= 1024 entries, zero-terminated. */
+/* Debug (SV_MEGA_DEBUG=1): timeline records of CTA 0 for the first token of the last persistent-decode launch,
+ * `id << 48 | SM clock` (ids: sv_decode_flow.cu); entries [0,4096) consumer thread 0, [4096,8192) producer warp;
+ * unused entries are 0; n <= 8192. */
 SV_API int sv_debug_read_timeline(sv_engine* e, long long* out_host, int32_t n);
 /* Device time (ms) of the last sv_generate decode loop and its step count, from CUDA events
  * recorded on the launching stream. */

@@ -183,6 +183,26 @@ class OracleStarVector:
         return out.logits[:, t0 - 1:, :].float()
 
 
+    @torch.no_grad()
+    def teacher_forced_logits_at(self, image: torch.Tensor, prompt_ids: Sequence[int], forced: torch.Tensor,
+                                 steps: Sequence[int]) -> torch.Tensor:
+        """`teacher_forced_logits(...)[:, steps]` without materialising the other positions' logits (long contexts):
+        one full forward of the decoder body, lm_head on the selected positions only.  `[B, len(steps), V]` fp32."""
+        inputs_embeds, _, _ = self.prepare_generation_inputs(image, prompt_ids)
+        t0 = inputs_embeds.shape[1]
+        emb = torch.cat([inputs_embeds, self._embed(forced)], dim=1)
+        hidden = self._body(inputs_embeds=emb, use_cache=False).last_hidden_state
+        idx = torch.tensor([t0 - 1 + int(j) for j in steps])
+        return self.llm.lm_head(hidden[:, idx]).float()
+
+    def _embed(self, ids):
+        return self.llm.transformer.wte(ids)
+
+    @property
+    def _body(self):
+        return self.llm.transformer
+
+
 # ======================================================================================================
 # StarVector v2 (8B family): SigLIP vision tower + Adapter + StarCoder2 — reference models/starvector_v2.py,
 # image_encoder.py:32-48,108-109 and llm/starcoder2.py:19-32.  Both towers are the installed transformers
@@ -265,9 +285,15 @@ class OracleStarVectorV2(OracleStarVector):
     def generation_kwargs(self, base, stop_ids):
         kw = super().generation_kwargs(base, stop_ids)
         kw.pop("pad_token_id")                                                     # _get_im2svg_specific_kwargs -> {} (v2:53-57)
-        kw.pop("early_stopping")
-        kw["early_stopping"] = True if kw["num_beams"] > 1 else False
+        kw.pop("early_stopping")                                                   # v2 passes none: HF default (False) applies
         return kw
+
+    def _embed(self, ids):
+        return self.llm.model.embed_tokens(ids)
+
+    @property
+    def _body(self):
+        return self.llm.model
 
     @torch.no_grad()
     def teacher_forced_logits(self, image, prompt_ids, forced):

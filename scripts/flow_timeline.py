@@ -33,33 +33,56 @@ prompt = torch.tensor([[44, 5678]] * a.batch, dtype=torch.int32).cuda()
 for rep in range(2):
     eng.encode_images(img)
     eng.prefill(prompt)
-    ids = torch.full((a.batch,), 17, dtype=torch.int32, device="cuda")
-    for _ in range(a.ctx):
-        eng.decode_step(ids)
+    if a.ctx:      # long-context timeline: teacher-forced single-token launches; the records are of the last one
+        ids = torch.full((a.batch,), 17, dtype=torch.int32, device="cuda")
+        for _ in range(a.ctx):
+            eng.decode_step(ids, return_logits=False)
+        torch.cuda.synchronize()
+        continue
     out = eng.generate(GenerationParams(max_new_tokens=a.new, eos_token_id=None, pad_token_id=49152))
     torch.cuda.synchronize()
     ms, steps = eng.last_decode_timing()
     print(f"rep {rep}: {steps} decode steps in {ms:.3f} ms -> {ms / max(steps, 1) * 1000:.1f} us/step", flush=True)
-tl = eng.debug_timeline()
-L = d.n_layer
-names = ["qkv.ready", "qkv.done", "attn.done", "merge.done", "cproj.ready", "cproj.done", "fc.ready", "fc.done", "fc2.ready", "fc2.done"]
-if len(tl) >= 10 * L + 2:
-    per = {n: 0 for n in names}
-    prev = tl[0]
-    for l in range(L):
-        for k, n in enumerate(names):
-            v = tl[l * 10 + k]
-            per[n] += v - prev
-            prev = v
-    tail = tl[10 * L:]
-    total = tl[-1] - tl[0]
-    print(f"stamps {len(tl)}  total {total} cycles for the first token of the launch (CTA 0)")
-    for n in names:
-        print(f"  {n:12s} {per[n] / L:9.0f} cycles/layer  ({per[n] * 100.0 / total:5.1f} % of the token)")
-    print("  tail (lm_head.ready, lm_head.done, select.done) deltas:", [tail[i] - (tail[i - 1] if i else tl[10 * L - 1]) for i in range(len(tail))])
+raw = eng.debug_timeline(8192, raw=True)
+KIND = ["qkv", "c_proj", "fc", "fc2", "lm_head"]
+SUB = {1: "enter", 2: "x_ready", 3: "ln_done", 4: "w0_landed", 5: "w_last", 6: "done"}
+ATT = {40: "att.enter", 41: "att.q_ready", 42: "att.blocks", 43: "att.tree", 44: "att.stored", 46: "merge.done", 47: "select.done"}
+
+
+def name_of(i):
+    if i in ATT:
+        return ATT[i]
+    if i >= 64:
+        k = i - 64
+        return f"P.{KIND[k // 2]}.start" if k % 2 == 0 and k // 2 < len(KIND) else f"P.{k}"
+    return f"{KIND[i // 8]}.{SUB.get(i % 8, i % 8)}"
+
+
+cons = [((v >> 48) & 0xffff, v & 0xffffffffffff) for v in raw[:4096] if v]
+prod = [((v >> 48) & 0xffff, v & 0xffffffffffff) for v in raw[4096:] if v]
+if cons:
+    t0 = cons[0][1]
+    total = cons[-1][1] - t0
+    # per-record-name: mean delta from the previous consumer record, over the layers
+    sums, counts, order = {}, {}, []
+    prev = t0
+    for i, t in cons:
+        n = name_of(i)
+        if n not in sums:
+            sums[n] = 0; counts[n] = 0; order.append(n)
+        sums[n] += t - prev; counts[n] += 1
+        prev = t
+    print(f"consumer records {len(cons)}, producer records {len(prod)}; first token of the launch: {total} cycles on CTA 0")
+    print("  record              n   mean delta from previous record (cycles)   share")
+    for n in order:
+        print(f"  {n:18s} {counts[n]:3d}   {sums[n] / counts[n]:10.0f}   {sums[n] * 100.0 / total:5.1f} %")
+    # producer lead: at every consumer 'enter' of a GEMV phase, had the producer already issued that phase's last slab?
+    if prod:
+        print("  producer (cycles after the consumer's first record): first 12:", [(name_of(i), t - t0) for i, t in prod[:12]])
+        print("  consumer first 16:", [(name_of(i), t - t0) for i, t in cons[:16]])
     if a.json:
-        json.dump({"cycles_per_layer": {n: per[n] / L for n in names}, "total_cycles": total, "stamps": tl, "ctx": a.ctx, "batch": a.batch},
-                  open(a.json, "w"))
+        json.dump({"consumer": [(name_of(i), t - t0) for i, t in cons], "producer": [(name_of(i), t - t0) for i, t in prod],
+                   "mean_delta": {n: sums[n] / counts[n] for n in order}, "total_cycles": total, "ctx": a.ctx, "batch": a.batch}, open(a.json, "w"))
 else:
-    print("timeline too short:", len(tl))
+    print("no timeline records (SV_MEGA_DEBUG unset or the dataflow kernel is not in use)")
 eng.close()

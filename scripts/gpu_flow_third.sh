@@ -1,0 +1,13 @@
+#!/bin/bash
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout ${TMO:-300} "$@" > gpurun_out/r02_$name.log 2>&1; echo "exit $? ($name)"; tail -n ${TAILN:-4} gpurun_out/r02_$name.log | cut -c1-1500; }
+TAILN=8 run c_engine python -m pytest tests/test_engine_gpu.py -q --tb=short -m gpu -x
+TAILN=55 run c_timeline python scripts/flow_timeline.py --new 8 --json gpurun_out/r02_flow_timeline_c.json
+for la in 0 8 16; do
+  SV_FLOW_L2AHEAD=$la TAILN=1 run c_bench_la$la python bench.py --steps 2 --warmup 3 --max-new-tokens 512 --no-cpu-baseline
+done
+SV_FLOW=2 TAILN=1 run c_bench_realloc python bench.py --steps 2 --warmup 3 --max-new-tokens 512 --no-cpu-baseline
+SV_FLOW=2 TAILN=50 run c_timeline_realloc python scripts/flow_timeline.py --new 8
+TMO=900 TAILN=12 run c_full1b python -m pytest tests/test_full_1b_gpu.py -q --tb=short -m gpu -x

@@ -68,7 +68,7 @@ def beam_search(engine: Engine, image: Optional[torch.Tensor], prompt_ids: Optio
     K = max(2, 1 + n_eos) * nb                                            # beams_to_keep
     top_mask = torch.zeros(K, dtype=torch.bool, device=dev)
     top_mask[:nb] = True
-    fill = (pad_token_id or eos_token_id) if eos_token_id is not None else -1
+    fill = (pad_token_id if pad_token_id is not None else eos_token_id) if eos_token_id is not None else -1   # HF: `pad if pad is not None`
     running_sequences = torch.full((B, nb, max_length), fill, dtype=torch.int64, device=dev)
     sequences = running_sequences.clone()
     running_beam_scores = torch.zeros((B, nb), dtype=torch.float32, device=dev)

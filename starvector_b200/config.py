@@ -91,6 +91,35 @@ def dims_8b(max_batch: int = 4, max_len: int = 16384, rope_theta: float = 1.0e6)
     )
 
 
+def refine_dims_from_state_dict(d: ModelDims, sd) -> ModelDims:
+    """Decoder dimensions as the CHECKPOINT has them (tensor shapes win over config fields): a v1 checkpoint whose
+    `max_length` differs from the decoder's `n_positions`, or any model size other than 1B / 8B, loads instead of
+    failing with a shape mismatch.  Only fields that a tensor shape determines are touched."""
+    v2 = d.variant == 1
+    pre = "model.svg_transformer.transformer." + ("model." if v2 else "transformer.")
+    emb = sd.get(pre + ("embed_tokens.weight" if v2 else "wte.weight"))
+    if emb is None:
+        return d
+    over = {"vocab": int(emb.shape[0]), "hidden": int(emb.shape[1])}
+    layer = pre + ("layers." if v2 else "h.")
+    over["n_layer"] = 1 + max(int(k[len(layer):].split(".")[0]) for k in sd if k.startswith(layer))
+    fc = sd.get(layer + "0.mlp.c_fc.weight")
+    if fc is not None:
+        over["n_inner"] = int(fc.shape[0])
+    over["n_head"] = over["hidden"] // d.head_dim
+    if v2:
+        kp = sd.get(layer + "0.self_attn.k_proj.weight")
+        if kp is not None:
+            over["n_kv_head"] = int(kp.shape[0]) // d.head_dim
+    else:
+        wpe = sd.get(pre + "wpe.weight")
+        if wpe is not None:
+            over["n_positions"] = int(wpe.shape[0])
+    out = dataclasses.replace(d, **over)
+    out.max_len = min(out.max_len, out.n_positions)
+    return out
+
+
 def dims_tiny_v2(max_batch: int = 4, max_len: int = 192, **over) -> ModelDims:
     """Few-MB model with the 8B family's structure (SigLIP tower, GQA group 2, RoPE, sliding window 24)."""
     d = ModelDims(

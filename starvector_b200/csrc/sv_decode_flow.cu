@@ -38,8 +38,13 @@ using namespace mega;
 constexpr int MAXS = 64;                      // attention key splits per (image, kv head)
 constexpr int FLOW_OFF_STAT = OFF_STAT;       // [2][NWC][8] floats: needs 2x the mega layout's room
 constexpr int FLOW_OFF_BAR = FLOW_OFF_STAT + 2 * NWC * 8 * 4;
-constexpr int FLOW_OFF_TOK = FLOW_OFF_BAR + 2 * STAGES * 8;
-constexpr int FLOW_SMEM_BYTES = FLOW_OFF_TOK + 64 + 128;
+constexpr int FLOW_OFF_TOK = FLOW_OFF_BAR + 2 * STAGES * 8 + 4 * 8;      // + 2 full / 2 empty barriers of the LayerNorm ring
+constexpr int LN_MAX_H = 2 * KS_MAX;          // LayerNorm width the parameter ring holds (the flow kernel needs H <= 2048)
+constexpr int LN_SLOT_BYTES = 2 * LN_MAX_H * 2;                          // weight row + bias row, bf16
+constexpr int FLOW_OFF_STATE = FLOW_OFF_TOK + 64;                        // CTA 0: GenState + GenParamsDev working copies
+constexpr int FLOW_OFF_LN = (FLOW_OFF_STATE + (int)sizeof(GenState) + (int)sizeof(GenParamsDev) + 127) & ~127;   // [2][LN_SLOT_BYTES]
+constexpr int FLOW_SMEM_BYTES = FLOW_OFF_LN + 2 * LN_SLOT_BYTES + 128;
+static_assert(FLOW_SMEM_BYTES <= 232448, "dataflow decode kernel: shared memory over the 227 KB per-CTA limit");
 
 struct FlowArgs {
   const Layer* layers;
@@ -55,6 +60,7 @@ struct FlowArgs {
   uint8_t* seen;
   int32_t *next_ids, *out_ids;
   int nsteps, step0, cur_len0, first_plain, do_select;
+  int l2_ahead;                  // weight slabs the producer asks L2 to fetch ahead of the shared-memory ring (0 = off)
   long long* dbg;                // optional: CTA 0 / thread 0 clock64() stamps of the first step
 };
 
@@ -109,20 +115,50 @@ struct FCtx {
   int dbg_i;
   bool slow_select;   // repetition penalty armed: the select phase scans the full logits row
 };
-SV_DEVINL void stamp(FCtx& cx) { if (cx.dbg && cx.dbg_i < 1000) cx.dbg[cx.dbg_i++] = clock64(); }
+// timeline records (SV_MEGA_DEBUG): [id << 48 | clock64], CTA 0 only; consumer thread 0 fills dbg[0..4096), the producer
+// warp's lane 0 dbg[4096..8192).  ids: 8 * kind + {1 enter, 2 x ready, 3 LayerNorm done, 4 first weight slab landed, 5 last
+// slab consumed, 6 outputs stored} with kind 0 qkv, 1 c_proj, 2 fc, 3 mlp.c_proj, 4 lm_head; 40.. attention; 64 + 2 * kind
+// (+1) = producer starts (has issued) the kind's slabs.
+enum { ST_ENTER = 1, ST_XREADY = 2, ST_LN = 3, ST_W0 = 4, ST_WLAST = 5, ST_DONE = 6, ST_ATT_ENTER = 40, ST_ATT_Q = 41, ST_ATT_BLK = 42,
+       ST_ATT_TREE = 43, ST_ATT_DONE = 44, ST_MERGE_DONE = 46, ST_SELECT_DONE = 47, ST_PROD = 64 };
+constexpr int DBG_HALF = 4096;
+SV_DEVINL void stamp_raw(long long* dbg, int& i, int id) {
+  if (dbg && i < DBG_HALF) dbg[i++] = (long long)(((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xffffffffffffull));
+}
+SV_DEVINL void stamp(FCtx& cx, int id) { stamp_raw(cx.dbg, cx.dbg_i, id); }
 
 enum { EPI_LL = 0, EPI_LMHEAD = 2 };
+
+// LayerNorm parameters ride the producer's schedule too: (weight, bias) rows land in a 2-slot shared-memory mini-ring one or
+// two phases before the consumers need them, instead of 16 dependent trips to HBM in the LayerNorm prologue.
+struct LnRing {
+  uint32_t base, full0, empty0, slot, phase;
+  SV_DEVINL void advance() { if (++slot == 2u) { slot = 0; phase ^= 1u; } }
+};
+SV_DEVINL void produce_ln(LnRing& lr, const bf16* ln_w, const bf16* ln_b, int N, int K, int cta, int ncta, int lane) {
+  if (make_plan(N, K, cta, ncta).ntile <= 0) return;          // the consumers skip the phase as well
+  if (lane == 0) {
+    const uint32_t fb = lr.full0 + 8u * lr.slot, dst = lr.base + lr.slot * LN_SLOT_BYTES;
+    mbar_wait(lr.empty0 + 8u * lr.slot, lr.phase ^ 1u);
+    mbar_expect_tx(fb, (uint32_t)(4 * K));
+    bulk_g2s(dst, ln_w, (uint32_t)(2 * K), fb);
+    bulk_g2s(dst + LN_MAX_H * 2, ln_b, (uint32_t)(2 * K), fb);
+  }
+  lr.advance();
+}
 
 // ---- consumer: one GEMV phase  Y[B,N] = epi( LN?(X)[B,K] . W[N,K]^T ) on flagged activations.
 // X: flagged [B][K] carrying tag EX.  res (optional): flagged [B][N], tag ER.  EPI_LL: Y flagged [B][N], tag EY.
 // EPI_LMHEAD: plain bf16 logits + one flagged argmax partial per (tile, image).
-template <bool HAS_LN, int EPI>
-SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint32_t EX, const bf16* __restrict__ bias,
-                         const uint32_t* res, uint32_t ER, uint32_t* Y, uint32_t EY, int N, int K, int act,
-                         const bf16* __restrict__ ln_w, const bf16* __restrict__ ln_b, uint32_t gp) {
+// has_ln / epi are run-time (warp-uniform) switches on purpose: the kernel holds ONE copy of this code for its five call
+// patterns (a 256 KB kernel thrashed the instruction cache at every phase change).
+SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const int epi, const uint32_t* __restrict__ X, uint32_t EX,
+                         const bf16* __restrict__ bias, const uint32_t* res, uint32_t ER, uint32_t* Y, uint32_t EY, int N, int K, int act,
+                         uint32_t gp, int kind) {
   const FlowArgs& a = *cx.a;
   const Plan p = make_plan(N, K, cx.cta, cx.ncta);
-  if (p.ntile <= 0) return;                          // nothing to do here: go and wait where this CTA has work
+  if (p.ntile <= 0) return;
+  stamp(cx, 8 * kind + ST_ENTER);                          // nothing to do here: go and wait where this CTA has work
   const int warp = cx.warp, g = cx.g, t = cx.t;
   const int cps = p.KS >> 5;                         // 32-wide chunks per slot row
   const int cpws = (cps + NWC - 1) / NWC;            // chunks per warp per slot (<= CPW)
@@ -150,8 +186,8 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint
         if (bad) spin_guard(it);
       } while (bad);
     }
-    stamp(cx);
-    if constexpr (HAS_LN) {
+    stamp(cx, 8 * kind + ST_XREADY);
+    if (has_ln) {
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 2 * CPW; ++i) {
@@ -188,6 +224,8 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint
 #pragma unroll
       for (int w = 0; w < NWC; ++w) var += cx.stat[NWC * 8 + w * 8 + g];
       const float rstd = 1.0f / sqrtf(var / (float)K + a.ln_eps);
+      mbar_wait(lr.full0 + 8u * lr.slot, lr.phase);          // staged by the producer warp, normally long ago
+      const uint32_t lnw = lr.base + lr.slot * LN_SLOT_BYTES + 16 * t, lnb = lnw + LN_MAX_H * 2;
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -197,13 +235,17 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint
           float f[8], wf[8], bfv[8];
           unpack8(xr[ks * CPW + j], f);
           const int ch = okc ? ks * cps + cl : 0;
-          unpack8(ldg_cached(ln_w + ch * 32 + 8 * t), wf);
-          unpack8(ldg_cached(ln_b + ch * 32 + 8 * t), bfv);
+          unpack8(lds16(lnw + ch * 64), wf);
+          unpack8(lds16(lnb + ch * 64), bfv);
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = (row_ok && okc) ? (f[e] - mean) * rstd * wf[e] + bfv[e] : 0.f;
           xr[ks * CPW + j] = pack8(f);       // ln output is a bf16 tensor in the reference; 0 on padded chunks
         }
       }
+      __syncwarp();
+      if (cx.lane == 0) mbar_arrive(lr.empty0 + 8u * lr.slot);
+      lr.advance();
+      stamp(cx, 8 * kind + ST_LN);
     }
   }
 
@@ -216,11 +258,14 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint
     const bool eok = threadIdx.x < 128 && en < p.R && ecol < N && emm < a.B;
     uint32_t rword = 0;
     if (res != nullptr && eok) rword = ld_rlx32(res + (int64_t)emm * N + ecol);
+    float bias_v = 0.f;                                  // fetched now: an HBM miss here must not sit behind the last MMA
+    if (bias != nullptr && eok) bias_v = __bfloat162float(bias[ecol]);
     if (!big_k) {
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         if (ks < p.nstg) {
           mbar_wait(r.full0 + 8u * r.slot, r.phase);
+          if (tl == 0 && ks == 0) stamp(cx, 8 * kind + ST_W0);
           const uint32_t sb = r.base + r.slot * SLOT_BYTES + g * p.pitch + t * 16;
 #pragma unroll
           for (int j = 0; j < CPW; ++j) {
@@ -238,31 +283,52 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint
         }
       }
     } else {
-      // K > 2048: activation fragments are fetched per slab from L2, one slab ahead of their use
-      uint4 xc[CPW], xn[CPW];
-      auto fetch = [&](int ks) {
+      // K > 2048: activation fragments are fetched per slab from L2, one slab ahead of their use.  The loads of slab
+      // ks + 1 are ISSUED before the MMAs of slab ks and only CHECKED after them, so the L2 round trip hides behind the
+      // weight wait + MMAs (checking at once cost one exposed round trip per slab: 8 per mlp.c_proj tile).
+      uint4 xc[CPW], xn[CPW], ra[CPW], rb[CPW];
+      auto issue = [&](int ks) {
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) {
+          const int cl = warp + NWC * j;
+          if (row_ok && ks < p.nstg && j < cpws && cl < cps) {
+            const uint32_t* q = xp + (ks * cps + cl) * 32;
+            ra[j] = ld_rlx16(q); rb[j] = ld_rlx16(q + 4);
+          }
+        }
+      };
+      auto finish = [&](int ks) {                          // raw words -> fragments; spins (re-loading) until every tag matches
 #pragma unroll
         for (int j = 0; j < CPW; ++j) xn[j] = make_uint4(0u, 0u, 0u, 0u);
         if (row_ok && ks < p.nstg) {
-          uint32_t bad, it = 0;
-          do {
-            bad = 0;
+          uint32_t it = 0;
+          for (;;) {
+            uint32_t bad = 0;
 #pragma unroll
             for (int j = 0; j < CPW; ++j) {
               const int cl = warp + NWC * j;
-              if (j < cpws && cl < cps) bad |= ll_get8(xp + (ks * cps + cl) * 32, EX, xn[j]);
+              if (j < cpws && cl < cps) {
+                bad |= ((ra[j].x ^ EX) | (ra[j].y ^ EX) | (ra[j].z ^ EX) | (ra[j].w ^ EX) | (rb[j].x ^ EX) | (rb[j].y ^ EX) | (rb[j].z ^ EX) |
+                        (rb[j].w ^ EX)) >> 16;
+                xn[j].x = __byte_perm(ra[j].x, ra[j].y, 0x5410); xn[j].y = __byte_perm(ra[j].z, ra[j].w, 0x5410);
+                xn[j].z = __byte_perm(rb[j].x, rb[j].y, 0x5410); xn[j].w = __byte_perm(rb[j].z, rb[j].w, 0x5410);
+              }
             }
-            if (bad) spin_guard(it);
-          } while (bad);
+            if (!bad) break;
+            spin_guard(it);
+            issue(ks);
+          }
         }
       };
-      fetch(0);
-      if (tl == 0) stamp(cx);
+      issue(0);
+      finish(0);
+      if (tl == 0) stamp(cx, 8 * kind + ST_XREADY);
       for (int ks = 0; ks < p.nstg; ++ks) {
 #pragma unroll
         for (int j = 0; j < CPW; ++j) xc[j] = xn[j];
-        fetch(ks + 1);
+        issue(ks + 1);
         mbar_wait(r.full0 + 8u * r.slot, r.phase);
+        if (tl == 0 && ks == 0) stamp(cx, 8 * kind + ST_W0);
         const uint32_t sb = r.base + r.slot * SLOT_BYTES + g * p.pitch + t * 16;
 #pragma unroll
         for (int j = 0; j < CPW; ++j) {
@@ -276,9 +342,11 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint
         __syncwarp();
         if (cx.lane == 0) mbar_arrive(r.empty0 + 8u * r.slot);
         r.advance();
+        finish(ks + 1);
       }
     }
     // ---- tile finished: deterministic cross-warp split-K reduction + epilogue
+    if (tl == p.ntile - 1) stamp(cx, 8 * kind + ST_WLAST);
     float* rd = cx.red + (tl & 1) * (NWC * 16 * 8);
     rd[(warp * 16 + g) * 8 + 2 * t] = c[0]; rd[(warp * 16 + g) * 8 + 2 * t + 1] = c[1];
     rd[(warp * 16 + g + 8) * 8 + 2 * t] = c[2]; rd[(warp * 16 + g + 8) * 8 + 2 * t + 1] = c[3];
@@ -290,7 +358,7 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint
       for (int w = 0; w < NWC; ++w) acc += rd[(w * 16 + en) * 8 + emm];
       float v = 0.f;
       if (eok) {
-        const float bv = bias ? __bfloat162float(bias[ecol]) : 0.f;
+        const float bv = bias_v;
         float rv = 0.f;
         if (res != nullptr) {
           uint32_t it = 0;
@@ -299,13 +367,13 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint
         }
         v = epilogue_elem(acc, bv, act, res != nullptr, rv);
         const bf16 vb = __float2bfloat16_rn(v);
-        if constexpr (EPI == EPI_LL) {
+        if (epi == EPI_LL) {
           st_rlx32(Y + (int64_t)emm * N + ecol, EY | (uint32_t)__bfloat16_as_ushort(vb));
         } else {
           a.logits[(int64_t)emm * N + ecol] = vb;
         }
       }
-      if constexpr (EPI == EPI_LMHEAD) {
+      if (epi == EPI_LMHEAD) {
         // penalised selection reads the logits themselves: order them before the partial word that announces the tile
         // (all 16 stores a partial covers come from this half-warp)
         if (cx.slow_select) { __threadfence(); __syncwarp(); }
@@ -328,16 +396,60 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, const uint32_t* __restrict__ X, uint
     }
     // red[] is double-buffered by tile parity: one barrier per tile
   }
-  stamp(cx);
+  stamp(cx, 8 * kind + ST_DONE);
 }
 
-// ---- attention, hop 1: split-KV partials.  item = (image, kv head, key range c); the 8 consumer warps of the owning CTA
-// take one 32-key block each.  q (and the current token's k, v) come from the flagged QKV vector.
+// ---- attention, hop 1.  item = (image, kv head, key range c) = one CTA.
+// Two sub-phases with different work splits, so that no (m, l, acc) partial ever has to be merged across warps:
+//   1. keys split over warps: warp w computes S = q.K^T for key blocks w (and w + 8) of the item on the tensor cores
+//      (the <= 16 query heads of the kv head are the MMA M dimension), the row maxima go through shared memory, and with the
+//      item-wide maximum every warp turns its scores into P = exp2(S - M) once; P is parked in shared memory in exactly the
+//      register layout the P.V MMA wants as its A operand (so there is no transpose);
+//   2. output dims split over warps: warp w computes out[:, 16w .. 16w+15] = P . V over ALL keys of the item: it owns a
+//      disjoint slice of the output, its V^T rows are 16-byte coalesced loads that are issued before the softmax finishes.
+// One item covers <= 16 key blocks (512 keys).  Up to 512 keys of context a single item holds the whole row: it
+// normalises and writes the attention output directly (no merge hop).  Longer rows are cut into items of <= 8 blocks
+// whose (m, l, acc) partials go to merge_flow as flagged fp32 words.
+constexpr int ATT_R = 2;                                  // key blocks per warp and item
+constexpr int ATT_BLKS = NWC * ATT_R;                     // key blocks per item
+constexpr int ATT_P_BYTES = ATT_BLKS * 2 * 32 * 16;       // P fragments: [block][h][lane] x 16 bytes
+constexpr int OFF_ATT_M = OFF_ATT + ATT_P_BYTES;          // float [NWC][16] row maxima, then [NWC][16] row sums
+static_assert(ATT_P_BYTES + 2 * NWC * 16 * 4 <= ATT_BYTES, "attention scratch must fit the mega layout's tree-merge buffer");
+
 SV_DEVINL void attn_split(int nkeys, int& nact, int& per) {
   const int nblk = (nkeys + 31) / 32;
+  if (nblk <= ATT_BLKS) { nact = 1; per = nblk; return; }
   nact = min(MAXS, (nblk + NWC - 1) / NWC);
   per = (nblk + nact - 1) / nact;
   nact = (nblk + per - 1) / per;
+}
+
+// S (log2 domain, scaled, masked) of one 32-key block: thread (g, t) gets keys kb + 8t + 2j + e for head rows g (s[j][e])
+// and g + 8 (s[j][2 + e]) -- the layout the P.V A operand needs (sv_attention.cu, fragment trick).
+SV_DEVINL void qk_block(const uint32_t (&qa)[D / 16][4], const bf16* __restrict__ kbase, int kb, int key_end, float scale_log2,
+                        float (&s)[4][4], int g, int t) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    int key = kb + 8 * (g >> 1) + 2 * j + (g & 1);
+    key = key < key_end ? key : key_end - 1;
+    const bf16* kp = kbase + (int64_t)key * D + 8 * t;
+#pragma unroll
+    for (int jj = 0; jj < D / 32; ++jj) {
+      const uint4 w = ldcg16(kp + 32 * jj);
+      mma_bf16_16816(s[j], qa[2 * jj][0], qa[2 * jj][1], qa[2 * jj][2], qa[2 * jj][3], w.x, w.y);
+      mma_bf16_16816(s[j], qa[2 * jj + 1][0], qa[2 * jj + 1][1], qa[2 * jj + 1][2], qa[2 * jj + 1][3], w.z, w.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool valid = (kb + 8 * t + 2 * j + e) < key_end;
+      s[j][e] = valid ? s[j][e] * scale_log2 : -INFINITY;
+      s[j][2 + e] = valid ? s[j][2 + e] * scale_log2 : -INFINITY;
+    }
+  }
 }
 
 SV_DEVINL void attention_flow(FCtx& cx, const Layer* L, int cur_len, uint32_t E, uint32_t gp) {
@@ -349,18 +461,22 @@ SV_DEVINL void attention_flow(FCtx& cx, const Layer* L, int cur_len, uint32_t E,
   int nact, per;
   attn_split(nkeys, nact, per);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
-  float* att = reinterpret_cast<float*>(cx.smem + OFF_ATT);
+  const uint32_t pbuf = smem_u32(cx.smem + OFF_ATT);
+  float* mbuf = reinterpret_cast<float*>(cx.smem + OFF_ATT_M);
+  float* lbuf = mbuf + NWC * 16;
   const unsigned long long T = tag32(gp);
   const int nitems = a.B * a.n_kv * nact;
+  stamp(cx, ST_ATT_ENTER);
   for (int item = cx.cta; item < nitems; item += cx.ncta) {
     const int c = item % nact, bk = item / nact, kvh = bk % a.n_kv, b = bk / a.n_kv;
-    const int blk0 = c * per, blk1 = min(nblk, blk0 + per);
-    float acc[D / 8][4], mrow[2], lrow[2];
-#pragma unroll
-    for (int nd = 0; nd < D / 8; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
-    mrow[0] = mrow[1] = -INFINITY; lrow[0] = lrow[1] = 0.f;
-    if (blk0 + warp < blk1) {
-      const uint32_t* qkv_row = a.qkv + (int64_t)b * a.qkv_cols;
+    const int blk0 = c * per, blk1 = min(nblk, blk0 + per), nb = blk1 - blk0;
+    bf16* kb_ = L->kc + (int64_t)bk * a.tcap * D;
+    bf16* vb_ = L->vc + (int64_t)bk * D * a.tcap;
+    const uint32_t* qkv_row = a.qkv + (int64_t)b * a.qkv_cols;
+    // ---- sub-phase 1: scores of this warp's key blocks
+    float s[ATT_R][4][4];
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (warp < nb) {
       const uint32_t* qrow = qkv_row + (int64_t)kvh * group * D;
       uint32_t qa[D / 16][4];
       {
@@ -383,11 +499,11 @@ SV_DEVINL void attention_flow(FCtx& cx, const Layer* L, int cur_len, uint32_t E,
           qa[2 * jj + 1][0] = lo[jj].z; qa[2 * jj + 1][1] = hi[jj].z; qa[2 * jj + 1][2] = lo[jj].w; qa[2 * jj + 1][3] = hi[jj].w;
         }
       }
-      bf16* kb_ = L->kc + (int64_t)bk * a.tcap * D;
-      bf16* vb_ = L->vc + (int64_t)bk * D * a.tcap;
-      // the warp that will read the newest key block appends the current token's k / v to the cache first
-      // (GPTBigCodeAttention.forward: key_value = cat(layer_past, key_value), vendored modeling_gpt_bigcode.py:265-267)
-      if (blk1 == nblk && ((nblk - 1 - blk0) % NWC) == warp && cur_len < a.tcap) {
+      stamp(cx, ST_ATT_Q);
+      // the warp that reads the newest key block appends the current token's k / v to the cache first
+      // (GPTBigCodeAttention.forward: key_value = cat(layer_past, key_value), vendored modeling_gpt_bigcode.py:265-267);
+      // the other warps read that V^T column only after the CTA barrier below
+      if (blk1 == nblk && ((nb - 1) % NWC) == warp && cur_len < a.tcap) {
         const uint32_t* kll = qkv_row + (int64_t)a.n_head * D + (int64_t)kvh * D + 4 * lane;
         const uint32_t* vll = kll + (int64_t)a.n_kv * D;
         uint4 kw, vw;
@@ -408,37 +524,118 @@ SV_DEVINL void attention_flow(FCtx& cx, const Layer* L, int cur_len, uint32_t E,
         __threadfence_block();
         __syncwarp();
       }
-      for (int blk = blk0 + warp; blk < blk1; blk += NWC)
-        attn_block(qa, kb_, vb_, a.tcap, blk * 32, min(nkeys, blk * 32 + 32), scale_log2, acc, mrow, lrow, g, t);
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r) {
+        const int bi = warp + r * NWC;
+        if (bi < nb) {
+          const int kb = (blk0 + bi) * 32;
+          qk_block(qa, kb_, kb, min(nkeys, kb + 32), scale_log2, s[r], g, t);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mx0 = fmaxf(mx0, fmaxf(s[r][j][0], s[r][j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[r][j][2], s[r][j][3]));
+          }
+        }
+      }
+      mx0 = quad_max(mx0); mx1 = quad_max(mx1);
     }
-    float lq[2] = {quad_sum(lrow[0]), quad_sum(lrow[1])};
-    // tree merge 8 -> 4 -> 2 -> 1 warps through a 4-partial shared buffer
-    if (warp >= 4) attn_store_to(att + (warp - 4) * PSZ, acc, mrow, lq, g, t);
+    if (t == 0) { mbuf[warp * 16 + g] = mx0; mbuf[warp * 16 + g + 8] = mx1; }
     consumer_sync();
-    if (warp < 4) attn_merge_from(att + warp * PSZ, acc, mrow, lq, g, t);
+    stamp(cx, ST_ATT_BLK);
+    // ---- item-wide row maxima, P = exp2(S - M) parked as MMA A fragments, row sums
+    float M0 = -INFINITY, M1 = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NWC; ++w) { M0 = fmaxf(M0, mbuf[w * 16 + g]); M1 = fmaxf(M1, mbuf[w * 16 + g + 8]); }
+    float rs0 = 0.f, rs1 = 0.f;
+    if (warp < nb) {
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r) {
+        const int bi = warp + r * NWC;
+        if (bi < nb) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s[r][j][0] = exp2f(s[r][j][0] - M0); s[r][j][1] = exp2f(s[r][j][1] - M0);
+            s[r][j][2] = exp2f(s[r][j][2] - M1); s[r][j][3] = exp2f(s[r][j][3] - M1);
+            rs0 += s[r][j][0] + s[r][j][1]; rs1 += s[r][j][2] + s[r][j][3];
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint4 pa;
+            pa.x = pack_bf16x2(s[r][2 * h][0], s[r][2 * h][1]);
+            pa.y = pack_bf16x2(s[r][2 * h][2], s[r][2 * h][3]);
+            pa.z = pack_bf16x2(s[r][2 * h + 1][0], s[r][2 * h + 1][1]);
+            pa.w = pack_bf16x2(s[r][2 * h + 1][2], s[r][2 * h + 1][3]);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pbuf + ((bi * 2 + h) * 32 + lane) * 16), "r"(pa.x), "r"(pa.y),
+                         "r"(pa.z), "r"(pa.w) : "memory");
+          }
+        }
+      }
+    }
+    rs0 = quad_sum(rs0); rs1 = quad_sum(rs1);
+    if (t == 0) { lbuf[warp * 16 + g] = rs0; lbuf[warp * 16 + g + 8] = rs1; }
     consumer_sync();
-    if (warp == 2 || warp == 3) attn_store_to(att + (warp - 2) * PSZ, acc, mrow, lq, g, t);
-    consumer_sync();
-    if (warp < 2) attn_merge_from(att + warp * PSZ, acc, mrow, lq, g, t);
-    consumer_sync();
-    if (warp == 1) attn_store_to(att, acc, mrow, lq, g, t);
-    consumer_sync();
-    if (warp == 0) {
-      attn_merge_from(att, acc, mrow, lq, g, t);
-      unsigned long long* ws = a.part + ((int64_t)bk * MAXS + c) * PSZ;
-      if (t == 0) {
-        st_rlx64(ws + g, fword(mrow[0], T)); st_rlx64(ws + g + 8, fword(mrow[1], T));
-        st_rlx64(ws + 16 + g, fword(lq[0], T)); st_rlx64(ws + 16 + g + 8, fword(lq[1], T));
+    // ---- sub-phase 2: out[:, 16 * warp + {0..15}] = P . V over every key block of the item
+    float acc[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    const bf16* v0 = vb_ + (int64_t)(16 * warp + g) * a.tcap + blk0 * 32 + 8 * t;       // V^T row of n-tile 0; n-tile 1: + 8 rows
+#pragma unroll 1
+    for (int b0 = 0; b0 < nb; b0 += 4) {
+      uint4 vv[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (b0 + i < nb) {
+          vv[i][0] = ldcg16(v0 + (b0 + i) * 32);
+          vv[i][1] = ldcg16(v0 + 8 * (int64_t)a.tcap + (b0 + i) * 32);
+        }
       }
 #pragma unroll
-      for (int nd = 0; nd < D / 8; ++nd) {
-        unsigned long long* p0 = ws + 32 + g * D + 8 * nd + 2 * t;
-        unsigned long long* p1 = ws + 32 + (g + 8) * D + 8 * nd + 2 * t;
-        st_rlx64(p0, fword(acc[nd][0], T)); st_rlx64(p0 + 1, fword(acc[nd][1], T));
-        st_rlx64(p1, fword(acc[nd][2], T)); st_rlx64(p1 + 1, fword(acc[nd][3], T));
+      for (int i = 0; i < 4; ++i) {
+        if (b0 + i < nb) {
+          const uint4 p0 = lds16(pbuf + (((b0 + i) * 2 + 0) * 32 + lane) * 16), p1 = lds16(pbuf + (((b0 + i) * 2 + 1) * 32 + lane) * 16);
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            mma_bf16_16816(acc[n], p0.x, p0.y, p0.z, p0.w, vv[i][n].x, vv[i][n].y);
+            mma_bf16_16816(acc[n], p1.x, p1.y, p1.z, p1.w, vv[i][n].z, vv[i][n].w);
+          }
+        }
       }
     }
-    consumer_sync();
+    float L0 = 0.f, L1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < NWC; ++w) { L0 += lbuf[w * 16 + g]; L1 += lbuf[w * 16 + g + 8]; }
+    stamp(cx, ST_ATT_TREE);
+    if (nact == 1) {
+      // the whole row was in this item: normalise and publish the attention output (bf16, like the reference's attn_output)
+      uint32_t* orow = a.att + (int64_t)b * a.n_head * D + (int64_t)kvh * group * D;
+      const float i0 = 1.0f / L0, i1 = 1.0f / L1;
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int d = 16 * warp + 8 * n + 2 * t;
+        if (g < group) {
+          st_rlx32(orow + g * D + d, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][0] * i0)));
+          st_rlx32(orow + g * D + d + 1, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][1] * i0)));
+        }
+        if (g + 8 < group) {
+          st_rlx32(orow + (g + 8) * D + d, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][2] * i1)));
+          st_rlx32(orow + (g + 8) * D + d + 1, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][3] * i1)));
+        }
+      }
+    } else {
+      unsigned long long* ws = a.part + ((int64_t)bk * MAXS + c) * PSZ;
+      if (warp == 0 && t == 0) {
+        st_rlx64(ws + g, fword(M0, T)); st_rlx64(ws + g + 8, fword(M1, T));
+        st_rlx64(ws + 16 + g, fword(L0, T)); st_rlx64(ws + 16 + g + 8, fword(L1, T));
+      }
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int d = 16 * warp + 8 * n + 2 * t;
+        st_rlx64(ws + 32 + g * D + d, fword(acc[n][0], T)); st_rlx64(ws + 32 + g * D + d + 1, fword(acc[n][1], T));
+        st_rlx64(ws + 32 + (g + 8) * D + d, fword(acc[n][2], T)); st_rlx64(ws + 32 + (g + 8) * D + d + 1, fword(acc[n][3], T));
+      }
+    }
+    stamp(cx, ST_ATT_DONE);
+    consumer_sync();                                      // the scratch is reused by the CTA's next item
   }
 }
 
@@ -448,6 +645,7 @@ SV_DEVINL void merge_flow(FCtx& cx, int cur_len, uint32_t E, uint32_t gp) {
   const int group = a.n_head / a.n_kv;
   int nact, per;
   attn_split(cur_len + 1, nact, per);
+  if (nact == 1) return;                               // the single item published the output itself
   const unsigned long long T = tag32(gp);
   const int ntasks = a.B * a.n_head * (D / 32);
   for (int task = cx.cta + cx.ncta * cx.warp; task < ntasks; task += cx.ncta * NWC) {
@@ -518,10 +716,12 @@ SV_DEVINL void select_flow(FCtx& cx, int ntiles, uint32_t gp, int next_pos, uint
   const FlowArgs& a = *cx.a;
   AmaxPair* sm = reinterpret_cast<AmaxPair*>(cx.red);
   int* s_tok = reinterpret_cast<int*>(cx.smem + FLOW_OFF_TOK);
+  GenState* st = reinterpret_cast<GenState*>(cx.smem + FLOW_OFF_STATE);          // working copies (decode_flow_kernel prologue):
+  const GenParamsDev* prm = reinterpret_cast<const GenParamsDev*>(st + 1);         // no global round trips in the bookkeeping
   const int tid = threadIdx.x;
-  const float rp = a.params->rep_penalty;
+  const float rp = prm->rep_penalty;
   const uint32_t T16 = tag16(gp) >> 16;
-  const bool done = a.state->done != 0;            // only this CTA ever writes the state during the launch
+  const bool done = st->done != 0;                 // only this CTA ever writes the state during the launch
   for (int b = 0; b < a.B; ++b) {
     AmaxPair best{-INFINITY, 0x7fffffff};
     // the partial words double as "this tile's logits are complete" (the penalised path fenced before writing them)
@@ -571,9 +771,89 @@ SV_DEVINL void select_flow(FCtx& cx, int ntiles, uint32_t gp, int next_pos, uint
     }
   }
   consumer_sync();
-  if (tid == 0 && !done) select_apply_tokens(s_tok, a.B, a.vocab, a.state, a.params, a.seen, a.next_ids, a.out_ids, 1);
+  if (tid == 0 && !done) {
+    select_apply_tokens(s_tok, a.B, a.vocab, st, prm, a.seen, a.next_ids, a.out_ids, 1);
+    a.state->cur_len = st->cur_len; a.state->step = st->step; a.state->done = st->done;      // for the host / the next launch
+    for (int b = 0; b < a.B; ++b) a.state->unfinished[b] = st->unfinished[b];
+  }
   consumer_sync();
   embed_flow(cx, s_tok, next_pos, Enext);           // after `done` the other CTAs keep stepping until the launch ends
+}
+
+// ---- the static schedule: phase q of a token = layer q / 4, kind q % 4 (0 c_attn, 1 attn.c_proj, 2 mlp.c_fc, 3 mlp.c_proj);
+// q == 4 * n_layer is the lm_head
+struct PhaseW { const bf16 *W, *ln_w, *ln_b; int N, K, kind; };
+SV_DEVINL PhaseW phase_weights(const FlowArgs& a, int q) {
+  PhaseW w;
+  w.ln_w = nullptr; w.ln_b = nullptr;
+  if (q == 4 * a.n_layer) { w.W = a.lm_head; w.N = a.vocab; w.K = a.H; w.kind = 4; w.ln_w = a.lnf_w; w.ln_b = a.lnf_b; return w; }
+  const Layer* L = a.layers + (q >> 2);
+  w.kind = q & 3;
+  switch (w.kind) {
+    case 0: w.W = L->attn_w; w.N = a.qkv_cols; w.K = a.H; w.ln_w = L->ln1_w; w.ln_b = L->ln1_b; break;
+    case 1: w.W = L->proj_w; w.N = a.H; w.K = a.H; break;
+    case 2: w.W = L->fc_w; w.N = a.I; w.K = a.H; w.ln_w = L->ln2_w; w.ln_b = L->ln2_b; break;
+    default: w.W = L->fc2_w; w.N = a.H; w.K = a.I; break;
+  }
+  return w;
+}
+
+// Position of one CTA in the weight schedule of the launch: (token, phase, tile, k slab).  The producer warp keeps two
+// of them: `cur` feeds the shared-memory ring, `pf` runs `l2_ahead` slabs further and only asks L2 to fetch
+// (cp.async.bulk.prefetch.L2), so that HBM keeps streaming while the ring is full and the consumers sit in a
+// latency-bound phase (attention, hops): the ring then refills from L2 at L2 speed.
+struct WeightWalk {
+  int s, q, tl, ks, cta, ncta;
+  bool done;
+  PhaseW w;
+  Plan p;
+  SV_DEVINL void load(const FlowArgs& a) {
+    for (;;) {
+      if (s >= a.nsteps) { done = true; return; }
+      w = phase_weights(a, q);
+      p = make_plan(w.N, w.K, cta, ncta);
+      if (p.ntile > 0) return;
+      if (++q > 4 * a.n_layer) { q = 0; ++s; }
+    }
+  }
+  SV_DEVINL void init(const FlowArgs& a, int cta_, int ncta_) { s = 0; q = 0; tl = 0; ks = 0; cta = cta_; ncta = ncta_; done = false; load(a); }
+  SV_DEVINL bool at_phase_start() const { return tl == 0 && ks == 0; }
+  SV_DEVINL void next(const FlowArgs& a) {
+    if (++ks < p.nstg) return;
+    ks = 0;
+    if (++tl < p.ntile) return;
+    tl = 0;
+    if (++q > 4 * a.n_layer) { q = 0; ++s; }
+    load(a);
+  }
+  SV_DEVINL const bf16* row_ptr(int lane) const { return w.W + (int64_t)((p.tile0 + tl) * p.R + lane) * w.K + (int64_t)ks * p.KS; }
+  SV_DEVINL int rows() const { return min(p.R, w.N - (p.tile0 + tl) * p.R); }
+};
+
+// The producer also asks L2 for the K / V^T blocks this CTA's attention items of layer l will read (everything but the
+// current token, which arrives as flagged words): issued when the ring starts on the layer's c_attn weights, i.e. a few
+// microseconds before the attention phase, so its dependent loads hit L2 instead of HBM.
+SV_DEVINL void prefetch_kv_l2(const FlowArgs& a, const Layer* L, int cur_len, int cta, int ncta, int lane) {
+  if (cur_len <= 0) return;
+  const int nkeys = cur_len + 1, nblk = (nkeys + 31) / 32;
+  int nact, per;
+  attn_split(nkeys, nact, per);
+  const int nitems = a.B * a.n_kv * nact;
+  for (int item = cta; item < nitems; item += ncta) {
+    const int c = item % nact, bk = item / nact;
+    const int key0 = c * per * 32, key1 = min(cur_len, min(nblk, c * per + per) * 32);       // cached keys of the item
+    if (key1 <= key0) continue;
+    const char* kp = reinterpret_cast<const char*>(L->kc + ((int64_t)bk * a.tcap + key0) * D);
+    const int kbytes = (key1 - key0) * D * 2, piece = ((kbytes + 31) / 32 + 15) & ~15;
+    if (lane * piece < kbytes)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kp + lane * piece), "r"((uint32_t)min(piece, kbytes - lane * piece)) : "memory");
+    const int vbytes = ((key1 - key0) * 2 + 15) & ~15;
+#pragma unroll
+    for (int r = 0; r < D / 32; ++r) {
+      const char* vp = reinterpret_cast<const char*>(L->vc + ((int64_t)bk * D + lane + 32 * r) * a.tcap + key0);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vp), "r"((uint32_t)vbytes) : "memory");
+    }
+  }
 }
 
 template <bool REALLOC>
@@ -587,8 +867,14 @@ __global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow
   ring.full0 = smem_u32(smem + FLOW_OFF_BAR);
   ring.empty0 = ring.full0 + 8u * STAGES;
   ring.slot = 0; ring.phase = 0; ring.nslots = STAGES;
+  LnRing lnr;
+  lnr.base = smem_u32(smem + FLOW_OFF_LN);
+  lnr.full0 = ring.empty0 + 8u * STAGES;
+  lnr.empty0 = lnr.full0 + 16u;
+  lnr.slot = 0; lnr.phase = 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(ring.full0 + 8u * s, 1); mbar_init(ring.empty0 + 8u * s, NWC); }
+    for (int s = 0; s < 2; ++s) { mbar_init(lnr.full0 + 8u * s, 1); mbar_init(lnr.empty0 + 8u * s, NWC); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -599,15 +885,35 @@ __global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow
       if (warp > NWC) return;
     }
     // =========================== producer: the static weight schedule of the whole launch ===========================
-    for (int s = 0; s < a.nsteps; ++s) {
-      for (int l = 0; l < a.n_layer; ++l) {
-        const Layer* L = a.layers + l;
-        produce_phase(ring, L->attn_w, a.qkv_cols, a.H, cta, ncta, lane);
-        produce_phase(ring, L->proj_w, a.H, a.H, cta, ncta, lane);
-        produce_phase(ring, L->fc_w, a.I, a.H, cta, ncta, lane);
-        produce_phase(ring, L->fc2_w, a.H, a.I, cta, ncta, lane);
+    long long* pdbg = (a.dbg != nullptr && cta == 0 && lane == 0) ? a.dbg + DBG_HALF : nullptr;
+    int pi = 0;
+    WeightWalk cur, pf;
+    cur.init(a, cta, ncta);
+    pf.init(a, cta, ncta);
+    auto prefetch_slab = [&]() {
+      if (lane < pf.rows())
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.row_ptr(lane)), "r"((uint32_t)(pf.p.KS * 2)) : "memory");
+      pf.next(a);
+    };
+    for (int i = 0; i < a.l2_ahead && !pf.done; ++i) prefetch_slab();
+    while (!cur.done) {
+      if (a.l2_ahead > 0 && !pf.done) prefetch_slab();
+      if (cur.at_phase_start()) {
+        if (cur.s > 0) pdbg = nullptr;
+        stamp_raw(pdbg, pi, ST_PROD + 2 * cur.w.kind);
+        if (cur.w.ln_w != nullptr) produce_ln(lnr, cur.w.ln_w, cur.w.ln_b, cur.w.N, cur.w.K, cta, ncta, lane);
+        if (cur.w.kind == 0 && a.l2_ahead > 0) prefetch_kv_l2(a, a.layers + (cur.q >> 2), a.cur_len0 + cur.s, cta, ncta, lane);
       }
-      produce_phase(ring, a.lm_head, a.vocab, a.H, cta, ncta, lane);
+      const uint32_t fb = ring.full0 + 8u * ring.slot;
+      const int rows = cur.rows();
+      if (lane == 0) {
+        mbar_wait(ring.empty0 + 8u * ring.slot, ring.phase ^ 1u);
+        mbar_expect_tx(fb, (uint32_t)(rows * cur.p.KS * 2));
+      }
+      __syncwarp();
+      if (lane < rows) bulk_g2s(ring.base + ring.slot * SLOT_BYTES + lane * cur.p.pitch, cur.row_ptr(lane), (uint32_t)(cur.p.KS * 2), fb);
+      ring.advance();
+      cur.next(a);
     }
     return;   // in-flight bulk copies are all consumed (and thus complete) before the consumers exit
   }
@@ -620,6 +926,14 @@ __global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow
   cx.dbg = (a.dbg != nullptr && cta == 0 && threadIdx.x == 0) ? a.dbg : nullptr;
   cx.dbg_i = 0;
   cx.slow_select = a.params->rep_penalty != 1.0f;
+  if (cta == 0 && a.do_select) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + FLOW_OFF_STATE);
+    const uint32_t* s0 = reinterpret_cast<const uint32_t*>(a.state);
+    const uint32_t* s1 = reinterpret_cast<const uint32_t*>(a.params);
+    constexpr int n0 = (int)sizeof(GenState) / 4, n1 = (int)sizeof(GenParamsDev) / 4;
+    for (int i = threadIdx.x; i < n0 + n1; i += NCT) dst[i] = i < n0 ? s0[i] : s1[i - n0];
+    consumer_sync();
+  }
   const int ntiles_lm = make_plan(a.vocab, a.H, 0, ncta).ntiles;
   const uint32_t nl1 = (uint32_t)a.n_layer + 1u;
   if (a.first_plain && cta == 0) {
@@ -635,24 +949,34 @@ __global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow
     const uint32_t gs = (uint32_t)(a.step0 + s);
     const int cur_len = a.cur_len0 + s;
     if (s == 1) cx.dbg = nullptr;
-    for (int l = 0; l < a.n_layer; ++l) {
-      const Layer* L = a.layers + l;
-      const uint32_t gp = gs * nl1 + (uint32_t)l;
+    for (int q = 0; q <= 4 * a.n_layer; ++q) {
+      const int l = q >> 2;
+      const uint32_t gp = gs * nl1 + (uint32_t)l;          // the lm_head (q = 4 * n_layer) is "layer n_layer"
       const uint32_t E = tag16(gp), En = tag16(gp + 1u);
-      gemv_flow<true, EPI_LL>(cx, ring, a.xa, E, L->attn_b, nullptr, 0u, a.qkv, E, a.qkv_cols, a.H, 0, L->ln1_w, L->ln1_b, gp);
-      attention_flow(cx, L, cur_len, E, gp);
-      stamp(cx);
-      merge_flow(cx, cur_len, E, gp);
-      stamp(cx);
-      gemv_flow<false, EPI_LL>(cx, ring, a.att, E, L->proj_b, a.xa, E, a.xb, E, a.H, a.H, 0, nullptr, nullptr, gp);
-      gemv_flow<true, EPI_LL>(cx, ring, a.xb, E, L->fc_b, nullptr, 0u, a.hb, E, a.I, a.H, 2 /*gelu_tanh*/, L->ln2_w, L->ln2_b, gp);
-      gemv_flow<false, EPI_LL>(cx, ring, a.hb, E, L->fc2_b, a.xb, E, a.xa, En, a.H, a.I, 0, nullptr, nullptr, gp);
+      const PhaseW w = phase_weights(a, q);
+      const Layer* L = a.layers + (l < a.n_layer ? l : 0);
+      const uint32_t *X, *res = nullptr;
+      uint32_t *Y = nullptr, EY = E;
+      const bf16* bias = nullptr;
+      int act = 0, epi = EPI_LL;
+      switch (w.kind) {
+        case 0: X = a.xa; bias = L->attn_b; Y = a.qkv; break;
+        case 1: X = a.att; bias = L->proj_b; res = a.xa; Y = a.xb; break;
+        case 2: X = a.xb; bias = L->fc_b; Y = a.hb; act = 2 /*gelu_tanh*/; break;
+        case 3: X = a.hb; bias = L->fc2_b; res = a.xb; Y = a.xa; EY = En; break;
+        default: X = a.xa; epi = EPI_LMHEAD; break;
+      }
+      gemv_flow(cx, ring, lnr, w.ln_w != nullptr, epi, X, E, bias, res, E, Y, EY, w.N, w.K, act, gp, w.kind);
+      if (w.kind == 0) {
+        attention_flow(cx, L, cur_len, E, gp);
+        merge_flow(cx, cur_len, E, gp);
+        stamp(cx, ST_MERGE_DONE);
+      }
     }
     const uint32_t gp = gs * nl1 + (uint32_t)a.n_layer;
-    gemv_flow<true, EPI_LMHEAD>(cx, ring, a.xa, tag16(gp), nullptr, nullptr, 0u, nullptr, 0u, a.vocab, a.H, 0, a.lnf_w, a.lnf_b, gp);
     if (a.do_select && cta == 0) {
       select_flow(cx, ntiles_lm, gp, cur_len + 1, tag16((gs + 1u) * nl1));
-      stamp(cx);
+      stamp(cx, ST_SELECT_DONE);
     }
   }
 }
@@ -708,6 +1032,7 @@ cudaError_t launch_decode_flow(const FlowLaunch& m, cudaStream_t st) {
   a.xa = m.xa; a.xb = m.xb; a.qkv = m.qkv; a.att = m.att; a.hb = m.hb; a.part = m.part; a.amax = m.amax;
   a.state = m.state; a.params = m.params; a.seen = m.seen; a.next_ids = m.next_ids; a.out_ids = m.out_ids;
   a.nsteps = m.nsteps; a.step0 = m.step0; a.cur_len0 = m.cur_len0; a.first_plain = m.first_plain; a.do_select = m.do_select;
+  a.l2_ahead = m.l2_ahead;
   a.dbg = m.dbg;
   void* args[] = {&a};
   cudaError_t e;

@@ -89,6 +89,7 @@ struct sv_engine {
   size_t flow_bytes = 0;
   uint32_t *f_xa = nullptr, *f_xb = nullptr, *f_qkv = nullptr, *f_att = nullptr, *f_hb = nullptr;
   unsigned long long *f_part = nullptr, *f_amax = nullptr;
+  int flow_l2_ahead = 8;            // SV_FLOW_L2AHEAD: weight slabs per CTA the producer prefetches into L2 ahead of the ring
   int flow_epoch = 0;               // phase-tag epoch: steps run through the flow kernel since the buffers were cleared
   bf16 *kscratch = nullptr, *vscratch = nullptr;   // one layer of cache, for beam-search reorders
   bf16 *kcache, *vtcache;           // [layer][max_batch][n_kv][tcap][D] / [layer][max_batch][n_kv][D][tcap]
@@ -322,7 +323,7 @@ bool build_buffers(sv_engine* e) {
   const int64_t amax_rows = std::max(gemv_ntiles(d.vocab), gemv_ring_ntiles(d.vocab));   // either lm_head kernel's tile count
   AL(amax_val, amax_rows * 8); AL(amax_idx, amax_rows * 8);
   AL(attn_counters, B * d.n_kv_head);
-  AL(mega_layers, d.n_layer); AL(mega_barrier, 4); AL(mega_dbg, 1024);
+  AL(mega_layers, d.n_layer); AL(mega_barrier, 4); AL(mega_dbg, 8192);
   {
     // flagged exchange buffers of the dataflow decode kernel, cleared together when a sequence starts
     const size_t n_x = (size_t)B * H * 4, n_qkv = (size_t)B * e->qkv_cols * 4, n_hb = (size_t)B * I * 4;
@@ -562,6 +563,7 @@ FlowLaunch flow_launch_desc(sv_engine* e, int B) {
   m.state = e->state; m.params = e->params; m.seen = e->seen; m.next_ids = e->next_ids; m.out_ids = e->out_ids;
   m.dbg = e->mega_debug ? e->mega_dbg : nullptr;
   m.realloc = e->flow_realloc;
+  m.l2_ahead = e->flow_l2_ahead;
   return m;
 }
 
@@ -675,7 +677,9 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
   { const char* fl = getenv("SV_FLOW");          // dataflow persistent kernel: default for greedy decode; "0" = per-phase graph
     e->use_flow = !(fl && !strcmp(fl, "0")) && !e->use_mega;
-    e->flow_realloc = fl && !strcmp(fl, "2"); }  // "2" = three warpgroups + setmaxnreg
+    e->flow_realloc = fl && !strcmp(fl, "2");    // "2" = three warpgroups + setmaxnreg
+    const char* la = getenv("SV_FLOW_L2AHEAD");
+    if (la) e->flow_l2_ahead = std::max(0, std::min(64, atoi(la))); }
   { const char* sg = getenv("SV_STEP_GRAPH"); e->step_graph = sg && !strcmp(sg, "1"); }
   const char* at = getenv("SV_ATTN");             // "ticket" = global-scratch + atomic-ticket merge instead of the cluster/DSMEM merge
   if (at && !strcmp(at, "ticket")) e->use_cluster_attn = false;
@@ -1038,7 +1042,7 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
     const int chunk = (can_stop || cb) ? poll : 512;
     FlowLaunch m = flow_launch_desc(e, B);
     m.do_select = 1;
-    if (e->mega_debug) cudaMemsetAsync(e->mega_dbg, 0, 1024 * sizeof(long long), st);
+    if (e->mega_debug) cudaMemsetAsync(e->mega_dbg, 0, 8192 * sizeof(long long), st);
     int left = max_new - 1;
     bool first = true;
     while (left > 0 && !done) {
@@ -1191,7 +1195,7 @@ int sv_reorder_cache(sv_engine* e, const int32_t* src_rows, void* stream) {
 int64_t sv_launch_count(const sv_engine* e) { return e ? e->launches : 0; }
 
 int sv_debug_read_timeline(sv_engine* e, long long* out_host, int32_t n) {
-  if (!e || !out_host || n < 1 || n > 1024) return SV_ERR_INVALID;
+  if (!e || !out_host || n < 1 || n > 8192) return SV_ERR_INVALID;
   cudaError_t r = cudaMemcpy(out_host, e->mega_dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
   return r == cudaSuccess ? SV_OK : SV_ERR_CUDA;
 }

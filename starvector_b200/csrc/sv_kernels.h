@@ -184,6 +184,7 @@ struct FlowLaunch {
   int cur_len0;        // tokens in the KV cache when the launch starts
   int first_plain;     // 1: the first step's input is x_plain (plain bf16) and gets converted to flagged words
   int do_select;       // 1: greedy select + embed after every step; 0: stop after the logits (teacher forcing)
+  int l2_ahead;        // weight slabs per CTA prefetched into L2 ahead of the shared-memory ring (0 = off)
   long long* dbg;
   bool realloc;
 };

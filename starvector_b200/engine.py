@@ -267,10 +267,10 @@ class Engine:
     def describe(self) -> str:
         return self._lib.sv_engine_describe(self._h).decode()
 
-    def debug_timeline(self, n: int = 1024):
+    def debug_timeline(self, n: int = 1024, raw: bool = False):
         buf = (C.c_longlong * n)()
         self._ck(self._lib.sv_debug_read_timeline(self._h, buf, n))
-        return [int(v) for v in buf if v]
+        return [int(v) for v in buf] if raw else [int(v) for v in buf if v]
 
     def last_decode_timing(self) -> Tuple[float, int]:
         ms, steps = C.c_float(), C.c_int32()

@@ -19,7 +19,7 @@ from typing import Any, Dict, List, Optional
 
 import torch
 
-from .config import ModelDims, StarVectorConfig
+from .config import ModelDims, StarVectorConfig, refine_dims_from_state_dict
 from .engine import Engine, GenerationParams
 from .parallel import merge_generated
 from .preprocess import ImageTrainProcessor, SiglipImageProcessor
@@ -44,12 +44,46 @@ class _Transformer:
         if attention_mask is not None and not bool(torch.all(attention_mask == 1)):
             raise NotImplementedError("padded prefixes never occur on the im2svg path and are not built")
         o = self._o
-        params = o._gen_params(kw, prefix_len=inputs_embeds.shape[1])
+        params = self._hf_params(kw, prefix_len=inputs_embeds.shape[1])
         nb = int(kw.get("num_beams", 1))
         if nb > 1:
-            return o._beam_generate(params, kw, nb, inputs_embeds=inputs_embeds)
+            return o._beam_generate(params, kw, nb, inputs_embeds=inputs_embeds, early_stopping=bool(kw.get("early_stopping", False)))
         o.engine.prefill_embeds(inputs_embeds)
         return o.engine.generate(params).long()
+
+    _HANDLED = {"do_sample", "top_p", "temperature", "num_beams", "max_length", "max_new_tokens", "min_length", "repetition_penalty",
+                "length_penalty", "use_cache", "stopping_criteria", "early_stopping", "pad_token_id", "eos_token_id", "seed"}
+
+    def _hf_params(self, kw: Dict[str, Any], prefix_len: int) -> GenerationParams:
+        """HF `generate()` semantics for exactly the kwargs the reference passes (starvector_base.py:228-241, :292-295):
+        HF defaults (greedy, top_p = 1, no stop sequence) unless given; anything else is refused instead of ignored."""
+        o = self._o
+        unknown = sorted(set(kw) - self._HANDLED)
+        if unknown:
+            raise NotImplementedError(f"generate(): unsupported arguments {unknown}")
+        do_sample = bool(kw.get("do_sample", False))
+        max_new = kw.get("max_new_tokens")
+        if max_new is None:
+            max_new = int(kw.get("max_length", 20)) - prefix_len                # generation/utils.py:1629-1638
+        if max_new <= 0:
+            raise ValueError(f"Input length of input_ids is 0, but `max_length` is set to {max_new}. Increase max_length "
+                             "(it counts the visual prefix and the prompt).")
+        if int(kw.get("min_length", 0)) - prefix_len > 0:                       # :1655-1660: becomes max(min_length - prefix, 0)
+            raise NotImplementedError("min_length beyond the prefix (a MinLengthLogitsProcessor) is not built")
+        stop_ids: List[int] = []
+        for crit in (kw.get("stopping_criteria") or []):
+            stops = getattr(crit, "stops", None)                                # StoppingCriteriaSub(stops=[ids]) (:9-20)
+            if stops is None or len(stops) != 1:
+                raise NotImplementedError("only the reference's StoppingCriteriaSub with one stop sequence is supported")
+            stop_ids = [int(t) for t in (stops[0].tolist() if hasattr(stops[0], "tolist") else stops[0])]
+        eos = kw.get("eos_token_id", o.eos_token_id)
+        pad = kw.get("pad_token_id")
+        if pad is None:
+            pad = eos if eos is not None else o.svg_transformer.tokenizer.pad_token_id     # HF: pad falls back to eos
+        return GenerationParams(max_new_tokens=int(max_new), do_sample=do_sample, temperature=float(kw.get("temperature", 1.0)),
+                                top_p=float(kw.get("top_p", 1.0)) if do_sample else 1.0,
+                                repetition_penalty=float(kw.get("repetition_penalty", 1.0)), eos_token_id=eos, pad_token_id=pad,
+                                stop_ids=stop_ids, stop_row0_only=True, seed=int(kw.get("seed", o.seed)))
 
 
 class _SvgTransformer:
@@ -142,7 +176,7 @@ class StarVectorStarCoder:
         )
 
     def _beam_generate(self, params: GenerationParams, kw: Dict[str, Any], num_beams: int, image=None, prompt_ids=None,
-                       inputs_embeds=None) -> torch.Tensor:
+                       inputs_embeds=None, early_stopping: Optional[bool] = None) -> torch.Tensor:
         """num_beams > 1 (the reference default is 2, starvector_base.py:234): beam search / beam-sample with the
         caller's `length_penalty`; `early_stopping=True` for v1 (:292), HF's default False for v2
         (starvector_v2.py:53-57) — bookkeeping in beam_search.py."""
@@ -153,7 +187,8 @@ class StarVectorStarCoder:
             max_new_tokens=params.max_new_tokens, do_sample=params.do_sample, temperature=params.temperature,
             top_p=params.top_p, repetition_penalty=params.repetition_penalty,
             length_penalty=float(kw.get("length_penalty", 1.0)),
-            early_stopping=not self.v2,       # v1 passes early_stopping=True (:292); v2's specific kwargs are {} -> HF default False
+            # v1 passes early_stopping=True (:292); v2's specific kwargs are {} -> HF default False
+            early_stopping=(not self.v2) if early_stopping is None else early_stopping,
             eos_token_id=params.eos_token_id, pad_token_id=params.pad_token_id, stop_ids=params.stop_ids, seed=params.seed)
 
     # -- the path ------------------------------------------------------------------------
@@ -219,9 +254,7 @@ class StarVectorStarCoder:
             if image.shape[0] * G > self.engine.dims.max_batch:
                 raise ValueError(f"batch {image.shape[0]} x num_return_sequences {G} exceeds the engine's max_batch "
                                  f"{self.engine.dims.max_batch}")
-            kwargs = dict(kwargs, num_beams=1)
-        else:
-            kwargs.setdefault("num_beams", 1)
+            kwargs = dict(kwargs, num_beams=1)                 # :277-280 (only when num_return_sequences > 1)
         ids = self.generate_im2svg_ids({"image": image.repeat_interleave(G, dim=0) if G > 1 else image}, **kwargs)
         emb, _ = self.engine.encode_images(image, return_embeds=True)
         prompt_ids = self._tokenize_prompt(kwargs.get("prompt"), image.shape[0])
@@ -249,14 +282,23 @@ def read_checkpoint(path: str):
 
 
 def write_checkpoint(path: str, config: StarVectorConfig, state_dict: Dict[str, torch.Tensor]) -> None:
-    """config.json + model.safetensors; the tied `lm_head.weight` is not stored twice (train/util.py:68-77)."""
+    """config.json + model.safetensors.  A TIED `lm_head.weight` (equal to the token embedding) is not stored twice — the
+    reference pops it and re-ties at load (train/util.py:68-77); an un-tied head, which the engine supports, is kept so that
+    a save / load round trip cannot silently change the logits."""
     from safetensors.torch import save_file
 
     os.makedirs(path, exist_ok=True)
     with open(os.path.join(path, "config.json"), "w") as f:
         json.dump(config.to_dict(), f, indent=1)
-    save_file({k: v.contiguous() for k, v in state_dict.items() if not k.endswith("lm_head.weight")},
-              os.path.join(path, "model.safetensors"))
+
+    def tied(k: str) -> bool:
+        if not k.endswith("lm_head.weight"):
+            return False
+        pre = k[: -len("lm_head.weight")]
+        emb = next((state_dict[c] for c in (pre + "transformer.wte.weight", pre + "model.embed_tokens.weight") if c in state_dict), None)
+        return emb is not None and emb.shape == state_dict[k].shape and torch.equal(emb, state_dict[k])
+
+    save_file({k: v.contiguous() for k, v in state_dict.items() if not tied(k)}, os.path.join(path, "model.safetensors"))
 
 
 class StarVectorForCausalLM:
@@ -267,14 +309,14 @@ class StarVectorForCausalLM:
     def __init__(self, config: StarVectorConfig, state_dict: Dict[str, torch.Tensor], device: int = 0,
                  max_batch: int = 8, max_len: Optional[int] = None, tokenizer_path: Optional[str] = None):
         self.config = config
-        dims = config.to_dims(max_batch=max_batch, max_len=max_len)
+        dims = refine_dims_from_state_dict(config.to_dims(max_batch=max_batch, max_len=max_len), state_dict)
         self.dims = dims
         engine = Engine(dims, device)
         engine.load_state_dict(state_dict)
         v2 = dims.variant == 1
         wte = state_dict[(DEC2 + "embed_tokens.weight") if v2 else (DEC + "wte.weight")].to(device=engine.device,
                                                                                                dtype=torch.bfloat16)
-        tok = load_tokenizer(tokenizer_path, dims.vocab)
+        tok = load_tokenizer(tokenizer_path, dims.vocab, v2=v2)
         self.model = StarVectorStarCoder(config, engine, tok, wte, v2=v2)     # v2 = StarVectorStarCoder2 (starvector_arch.py:137-145)
         self.device = engine.device
         self.dtype = torch.bfloat16

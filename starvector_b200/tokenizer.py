@@ -84,19 +84,34 @@ class SyntheticTokenizer:
         return [self.decode(r, skip_special_tokens) for r in rows]
 
 
-def load_tokenizer(path_or_none, vocab_size: int):
-    """Real tokenizer when a local directory provides one (prepared as llm/starcoder.py:40-53), else synthetic."""
+def load_tokenizer(path_or_none, vocab_size: int, v2: bool = False):
+    """Real tokenizer when a local directory provides one, prepared as the reference does — v1: llm/starcoder.py:40-53
+    (fast tokenizer, + [PAD], + 3 added tokens); v2: llm/starcoder2.py:36-53 (`use_fast=False`, + 4 added tokens incl.
+    `<svg-end>`, `padding_side = "left"`) — else the synthetic stand-in (3 / 4 added tokens after [PAD])."""
     import os
 
     if path_or_none and os.path.isdir(path_or_none) and any(
             os.path.exists(os.path.join(path_or_none, f)) for f in ("tokenizer.json", "vocab.json", "tokenizer_config.json")):
         from transformers import AutoTokenizer
 
-        tok = AutoTokenizer.from_pretrained(path_or_none, local_files_only=True)
+        if v2:
+            try:
+                tok = AutoTokenizer.from_pretrained(path_or_none, local_files_only=True, use_fast=False)
+            except (OSError, ValueError):           # a directory that only ships tokenizer.json has no slow tokenizer
+                tok = AutoTokenizer.from_pretrained(path_or_none, local_files_only=True)
+        else:
+            tok = AutoTokenizer.from_pretrained(path_or_none, local_files_only=True)
         if tok.eos_token_id is None:
             tok.add_special_tokens({"eos_token": "[EOS]"})
         if tok.pad_token_id is None:
             tok.add_special_tokens({"pad_token": "[PAD]"})
-        tok.add_tokens(["<svg-start>", "<image-start>", "<caption-start>"])
+        if v2:
+            tok.add_tokens(["<svg-start>", "<image-start>", "<caption-start>", "<svg-end>"])
+            tok.padding_side = "left"
+        else:
+            tok.add_tokens(["<svg-start>", "<image-start>", "<caption-start>"])
         return tok
-    return SyntheticTokenizer(vocab_size)
+    tok = SyntheticTokenizer(vocab_size, n_added=5 if v2 else 4)
+    if v2:
+        tok.padding_side = "left"
+    return tok

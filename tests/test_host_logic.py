@@ -164,3 +164,51 @@ def test_checkpoint_directory_round_trip(tmp_path):
     (tmp_path / "empty" / "config.json").write_text((tmp_path / "config.json").read_text())
     with pytest.raises(FileNotFoundError):
         read_checkpoint(str(tmp_path / "empty"))
+
+
+def test_untied_lm_head_survives_a_checkpoint_round_trip(tmp_path):
+    """The reference always re-ties (train/util.py:68-77); the engine also takes an un-tied head, so saving must keep it."""
+    from starvector_b200.config import StarVectorConfig
+    from starvector_b200.modeling import read_checkpoint, write_checkpoint
+
+    d = dims_tiny()
+    sd = dict(synthetic_state_dict(d, seed=0))
+    head = "model.svg_transformer.transformer.lm_head.weight"
+    write_checkpoint(str(tmp_path / "tied"), StarVectorConfig(), sd)
+    assert head not in read_checkpoint(str(tmp_path / "tied"))[1]                 # equal to wte: stored once
+    sd[head] = sd[head].clone() + 1.0
+    write_checkpoint(str(tmp_path / "untied"), StarVectorConfig(), sd)
+    back = read_checkpoint(str(tmp_path / "untied"))[1]
+    assert head in back and torch.equal(back[head], sd[head])
+
+
+def test_decoder_dims_follow_the_checkpoint_tensors():
+    """config.json fields that disagree with the tensors (max_length vs wpe rows, another model size) must not break loading."""
+    import dataclasses
+
+    from starvector_b200.config import dims_tiny_v2, refine_dims_from_state_dict
+
+    for d in (dims_tiny(), dims_tiny_v2()):
+        sd = synthetic_state_dict(d, seed=0)
+        wrong = dataclasses.replace(d, n_layer=7, n_inner=64, vocab=123, hidden=128 * 5, n_head=5,
+                                    n_positions=999 if d.variant == 0 else d.n_positions)
+        assert refine_dims_from_state_dict(wrong, sd) == d
+
+
+def test_v2_tokenizer_preparation(tmp_path):
+    """llm/starcoder2.py:36-53: four added tokens (incl. <svg-end>) and left padding; the synthetic stand-in mirrors both."""
+    from tokenizers import Tokenizer, models, pre_tokenizers, trainers
+    from transformers import PreTrainedTokenizerFast
+
+    from starvector_b200.tokenizer import load_tokenizer
+
+    tk = Tokenizer(models.BPE(unk_token="<unk>"))
+    tk.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tk.train_from_iterator(["<svg></svg>"] * 4, trainers.BpeTrainer(vocab_size=60, special_tokens=["<unk>"]))
+    PreTrainedTokenizerFast(tokenizer_object=tk, unk_token="<unk>").save_pretrained(str(tmp_path))
+    tok = load_tokenizer(str(tmp_path), vocab_size=500, v2=True)
+    assert tok.padding_side == "left"
+    for t in ("<svg-start>", "<image-start>", "<caption-start>", "<svg-end>"):
+        assert len(tok.encode(t)) == 1
+    syn = load_tokenizer(None, 500, v2=True)
+    assert isinstance(syn, SyntheticTokenizer) and syn.padding_side == "left" and syn.pad_token_id == 495
