@@ -154,7 +154,7 @@ class StarVectorStarCoder:
 
     def _gen_params(self, kw: Dict[str, Any], prefix_len: int) -> GenerationParams:
         """`_get_generation_kwargs` (:223-241) + `_get_im2svg_specific_kwargs` (:289-295) + HF length fix-up."""
-        do_sample = bool(kw.get("use_nucleus_sampling", kw.get("do_sample", True)))
+        do_sample = bool(kw.get("use_nucleus_sampling", True))                # :231 — a `do_sample` kwarg is not in the whitelist
         max_length = int(kw.get("max_length", 30))
         max_new = kw.get("max_new_tokens")
         if max_new is None:
