@@ -151,20 +151,23 @@ def weight_shapes(d: ModelDims) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
 
 def synthetic_state_dict(
     d: ModelDims, seed: int = 0, init: str = "hf_default", dtype: torch.dtype = torch.bfloat16,
-    logit_gain: float = 1.0,
+    logit_gain: float = 1.0, device=None,
 ) -> Dict[str, torch.Tensor]:
     """Seeded random checkpoint (CPU tensors in `dtype`).  `lm_head.weight` is tied to `wte`.
+
+    `device` (a CUDA device) draws the values on the GPU instead: same distributions, other values than the CPU stream,
+    for throughput runs of models no CPU oracle is run against (the 15 GB StarVector-8B replica in seconds, not minutes).
 
     `logit_gain` > 1 scales `wte` (hence the tied lm_head) to widen greedy top-1/top-2
     margins for the "peaked" parity configuration (SURVEY.md §7 hard parts (d)).
     """
     if init not in ("hf_default", "randomized"):
         raise ValueError(f"unknown init {init!r}")
-    g = torch.Generator().manual_seed(seed)
+    g = torch.Generator(device=device if device is not None else "cpu").manual_seed(seed)
     rnd = init == "randomized"
     sd: Dict[str, torch.Tensor] = {}
     for name, shape, kind in weight_shapes(d):
-        t = torch.empty(shape, dtype=torch.float32)
+        t = torch.empty(shape, dtype=torch.float32, device=device)
         if kind == "conv":
             fan_in = shape[1] * shape[2] * shape[3]
             b = 1.0 / math.sqrt(fan_in)

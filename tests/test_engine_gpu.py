@@ -201,3 +201,30 @@ def test_errors_are_python_exceptions(tiny):
     eng.prefill(torch.tensor([PROMPT] * 2))
     with pytest.raises(ValueError):
         eng.generate(GenerationParams(max_new_tokens=10 ** 6, pad_token_id=0))
+
+
+def test_per_row_stop_mode(tiny):
+    """`stop_row0_only=0` (the ABI's per-row mode; the reference's StoppingCriteriaSub only looks at row 0):
+    every row ends at ITS OWN stop sequence and is padded afterwards, the call ends when all rows have ended.
+    Oracle: the reference path run once per image (batch 1, where "row 0" is that image), re-rectangularised."""
+    d, sd, eng, o16, o32, img = tiny
+    n_new, pad = 24, d.vocab - 4
+    free, _ = oracle_greedy(o16, img, PROMPT, (), n_new)
+    stop = free[1, 3:5].tolist()                                   # a sequence row 1 emits early; row 0 may or may not
+    rows = []
+    for b in range(2):
+        r, _ = oracle_greedy(o16, img[b:b + 1], PROMPT, stop, n_new)
+        rows.append(r[0])
+    width = max(len(r) for r in rows)
+    ref = torch.full((2, width), pad, dtype=torch.long)
+    for b, r in enumerate(rows):
+        ref[b, :len(r)] = r
+    assert len(rows[1]) == 5                                       # row 1 stopped where the sequence first completes
+    eng.encode_images(img)
+    eng.prefill(torch.tensor([PROMPT] * 2))
+    got = eng.generate(GenerationParams(max_new_tokens=n_new, eos_token_id=0, pad_token_id=pad, stop_ids=stop, stop_row0_only=False,
+                                        poll_interval=1)).cpu().long()
+    if torch.equal(free, oracle_greedy(o16, img, PROMPT, (), n_new)[0]) and got.shape == ref.shape:
+        assert torch.equal(got, ref), (got.tolist(), ref.tolist())
+    else:                                                          # a tolerated bf16 flip changed a row: the stopped row must still be exact
+        assert got[1, :5].tolist() == rows[1].tolist() and (got[1, 5:] == pad).all()

@@ -113,3 +113,87 @@ def test_v2_facade_strings_match_oracle(tiny_v2):
     ref = o.generate_im2svg_ids(img, prompt, tok("</svg>")["input_ids"], **kw)
     assert got == tok.batch_decode(ref, skip_special_tokens=True)
     m.model.engine.close()
+
+
+def test_v2_two_beams_match_hf(tiny_v2):
+    """v2 passes no im2svg-specific kwargs (reference starvector_v2.py:53-57), so HF's default `early_stopping=False` is in
+    force: engine beams vs the oracle's (whose v2 kwargs no longer force early stopping)."""
+    import warnings
+
+    from oracle.pipeline import OracleStarVectorV2
+    from starvector_b200.beam_search import beam_search
+
+    g, d, sd, eng, img = tiny_v2
+    prompt, n_new, nb = g["prompt_ids"], 10, 2
+    o = OracleStarVectorV2(d, sd, dtype=torch.bfloat16)
+    emb, mask, _ = o.prepare_generation_inputs(img, prompt)
+    kw = o.generation_kwargs({"inputs_embeds": emb, "attention_mask": mask, "use_nucleus_sampling": False, "num_beams": nb,
+                              "max_length": d.query_length + len(prompt) + n_new}, ())
+    assert "early_stopping" not in kw
+    kw.pop("top_p"); kw.pop("temperature")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hyp = o.llm.generate(**kw, num_return_sequences=nb).view(2, nb, -1)
+    got = beam_search(eng, img, torch.tensor([prompt] * 2), num_beams=nb, max_new_tokens=n_new, early_stopping=False, eos_token_id=0,
+                      pad_token_id=0).cpu()
+
+    def strip(seq):
+        seq = seq.tolist()
+        while seq and seq[-1] == 0:
+            seq.pop()
+        return seq
+
+    hits = 0
+    for b in range(2):
+        mine = strip(got[b])
+        if any(mine == strip(hyp[b, k]) for k in range(nb)):
+            hits += 1
+            continue
+        # bf16 near-tie sent the search down another branch: the hypothesis must score as well under the oracle
+        def score(seq):
+            lg = o.teacher_forced_logits(img[b:b + 1], prompt, torch.tensor([seq]))[0, :len(seq)]
+            lp = torch.log_softmax(lg.float(), -1)
+            return sum(lp[t, seq[t]].item() for t in range(len(seq))) / len(seq)
+        s_m, s_r = score(mine), score(strip(hyp[b, 0]))
+        assert s_m >= s_r - 0.10 * abs(s_r), (b, s_m, s_r)
+    assert hits >= 1
+
+
+def test_8b_dims_two_layers_vs_oracle():
+    """Full StarVector-8B widths (SigLIP-L/16-384: 576 tokens x 1024 x 24 layers; StarCoder2: H 4608, 36 q / 4 kv heads,
+    I 18432, biases, RoPE) with TWO decoder layers so the fp32 CPU oracle stays fast; the sliding window is set to 512 so that
+    the 578-token prefill and the decode steps already run through the window mask.  Vision tower, adapter, prefill logits
+    and 8 teacher-forced decode steps against the oracle."""
+    import dataclasses
+
+    from oracle.pipeline import OracleStarVectorV2
+    from starvector_b200.config import dims_8b
+
+    d = dataclasses.replace(dims_8b(max_batch=2, max_len=640), n_layer=2, sliding_window=512, n_positions=1024, rope_theta=1.0e5)
+    sd = synthetic_state_dict(d, seed=3)
+    img = synthetic_images(d, 2, seed=4)
+    prompt = [44, 5678]
+    gen = torch.Generator().manual_seed(5)
+    forced = torch.randint(0, 49152, (2, 8), generator=gen)
+    eng = Engine(d, 0)
+    eng.load_state_dict(sd)
+    emb, vit = eng.encode_images(img, return_embeds=True, return_vit=True)
+    logits = [eng.prefill(torch.tensor([prompt] * 2), return_logits=True)]
+    for j in range(forced.shape[1]):
+        logits.append(eng.decode_step(forced[:, j]))
+    got = torch.stack(logits, dim=1).float().cpu()
+    emb, vit = emb.float().cpu(), vit.float().cpu()
+    eng.close()
+    torch.set_num_threads(os.cpu_count() or 1)
+    o = OracleStarVectorV2(d, sd, dtype=torch.float32)
+    ref_vit = o.image_encoder(img.float())
+    ref_emb = o.image_projection(ref_vit)
+    ref = o.teacher_forced_logits(img.float(), prompt, forced)
+    assert vit.shape == (2, 576, 1024) and emb.shape == (2, 576, 4608) and got.shape == ref.shape
+    for name, a, b, tol_max, tol_mean in (("vit", vit, ref_vit, 0.15, 0.012), ("adapter", emb, ref_emb, 0.12, 0.012), ("logits", got, ref, 0.25, 0.03)):
+        err = (a - b).abs()
+        scale = b.abs().mean().item()
+        assert err.max().item() < tol_max * max(1.0, scale * 4) and err.mean().item() < tol_mean * max(1.0, scale * 4), \
+            (name, err.max().item(), err.mean().item(), scale)
+    agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
+    assert agree >= 0.8, agree
