@@ -10,8 +10,11 @@ import json
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 os.environ.setdefault("SV_MEGA_DEBUG", "1")
+# the records are compiled out of the shipped library (they cost registers): python -m starvector_b200.build --variant timeline
+os.environ.setdefault("SV_LIB_PATH", os.path.join(ROOT, "starvector_b200", "libstarvector_b200_timeline.so"))
 import torch
 
 from starvector_b200.config import dims_1b

@@ -1,0 +1,11 @@
+#!/bin/bash
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout ${TMO:-300} "$@" > gpurun_out/r02_$name.log 2>&1; echo "exit $? ($name)"; tail -n ${TAILN:-4} gpurun_out/r02_$name.log | cut -c1-1500; }
+for la in 0 8 12; do
+  SV_FLOW_L2AHEAD=$la TAILN=1 run h_bench_la$la python bench.py --steps 2 --warmup 3 --max-new-tokens 512 --no-cpu-baseline --no-extras
+done
+TAILN=6 run h_engine python -m pytest tests/test_engine_gpu.py -q --tb=short -m gpu
+TAILN=48 run h_timeline python scripts/flow_timeline.py --new 8 --json gpurun_out/r02_flow_timeline_h.json
+SV_FLOW=3 TAILN=1 run h_bench_norealloc python bench.py --steps 2 --warmup 3 --max-new-tokens 512 --no-cpu-baseline --no-extras

@@ -33,6 +33,7 @@ DEVINL uint4 lds16(uint32_t addr) {
 struct P {
   const uint8_t* w;
   unsigned long long bytes_per_cta;   // each CTA streams its own contiguous region
+  unsigned long long window;          // != 0: the CTA re-reads only the first `window` bytes of its region (L2 resident)
   int rows, row_bytes, ksplit, pitch, stages, slot_bytes, consume, one_lane;   // ksplit: slots per tile (row length = ksplit * row_bytes)
   unsigned long long* sink;
 };
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(288, 1) ring_kernel(const P p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t base = smem_u32(smem), full0 = base + p.stages * p.slot_bytes, empty0 = full0 + 64;
+  const uint32_t base = smem_u32(smem), full0 = base + p.stages * p.slot_bytes, empty0 = full0 + 256;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(288, 1) ring_kernel(const P p) {
       __syncwarp();
       // the source walks the CTA's region in slot order; inside a slot, rows are row_stride apart (wrapping in the region)
       const unsigned long long tile = i / p.ksplit, kh = i % p.ksplit, row_stride = (unsigned long long)p.ksplit * p.row_bytes;
-      const uint8_t* s = src0 + tile * p.rows * row_stride + kh * p.row_bytes;
+      const unsigned long long off = tile * p.rows * row_stride + kh * p.row_bytes;
+      const uint8_t* s = src0 + (p.window ? off % p.window : off);
       if (p.one_lane) {
         if (lane == 0) for (int r = 0; r < p.rows; ++r) bulk_g2s(base + slot * p.slot_bytes + r * p.pitch, s + (unsigned long long)r * row_stride, p.row_bytes, fb);
       } else if (lane < p.rows) {
@@ -85,13 +87,13 @@ __global__ void __launch_bounds__(288, 1) ring_kernel(const P p) {
 }
 
 // ceiling: plain 16-byte streaming loads, 8 in flight per thread
-__global__ void __launch_bounds__(512, 1) ldg_kernel(const uint4* w, unsigned long long n16_per_cta, unsigned long long* sink) {
+__global__ void __launch_bounds__(512, 1) ldg_kernel(const uint4* w, unsigned long long n16_per_cta, unsigned long long* sink, unsigned long long win16 = 0) {
   const uint4* p = w + (unsigned long long)blockIdx.x * n16_per_cta;
   uint32_t acc = 0;
   for (unsigned long long i = threadIdx.x; i + 7 * 512 < n16_per_cta; i += 8 * 512) {
     uint4 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(p + i + j * 512));
+    for (int j = 0; j < 8; ++j) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(p + (win16 ? (i + j * 512) % win16 : (i + j * 512))));
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc ^= v[j].x ^ v[j].y ^ v[j].z ^ v[j].w;
   }
@@ -130,7 +132,7 @@ int main() {
     p.slot_bytes = v.rows * v.pitch; p.sink = sink;
     const unsigned long long payload = (unsigned long long)v.rows * v.row_bytes * v.ksplit;
     p.bytes_per_cta = total / ncta / payload * payload;
-    const int smem = v.stages * p.slot_bytes + 256 + 128;
+    const int smem = v.stages * p.slot_bytes + 512 + 128;
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
       cudaEventRecord(e0);
@@ -152,12 +154,56 @@ int main() {
     }
     printf("%-62s              %8.1f GB/s\n", "ld.global.nc v4, 512 threads x 8 in flight per SM", n16 * 16 * ncta / best * 1e-6);
   }
+  // L2-resident source: how fast can one SM's ring be filled when HBM is not involved?
+  {
+    float best = 1e30f;
+    const unsigned long long n16 = total / 16 / ncta;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0);
+      ldg_kernel<<<ncta, 512>>>(reinterpret_cast<const uint4*>(w), n16, sink, 131072 / 16);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    printf("ld.global.nc v4, 512 threads x 8 in flight, L2-RESIDENT (128 KB window per CTA): %8.1f GB/s = %.1f B/clk/SM\n", n16 * 16 * ncta / best * 1e-6,
+           n16 * 16 / best * 1e-6 / 1.9);
+  }
+  struct R { int rows, row_bytes, pitch, stages; };
+  for (const R& r : {R{8, 4096, 4160, 5}, R{4, 8192, 8256, 5}, R{2, 16384, 16448, 5}, R{1, 32768, 32768, 5}, R{1, 16384, 16384, 10}, R{16, 2048, 2112, 5}}) {
+    P p{};
+    p.w = w; p.rows = r.rows; p.row_bytes = r.row_bytes; p.pitch = r.pitch; p.stages = r.stages; p.consume = 1; p.slot_bytes = r.rows * r.pitch; p.sink = sink; p.ksplit = 1;
+    p.bytes_per_cta = (total / ncta) / 32768 * 32768; p.window = 131072;
+    const int smem = r.stages * p.slot_bytes + 640;
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0);
+      ring_kernel<<<ncta, 288, smem>>>(p);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    printf("%dx%dKB, %d stages, L2-RESIDENT source: %8.1f GB/s = %.1f B/clk/SM (%s)\n", r.rows, r.row_bytes / 1024, r.stages,
+           p.bytes_per_cta * ncta / best * 1e-6, p.bytes_per_cta / best * 1e-6 / 1.9, cudaGetErrorString(cudaGetLastError()));
+  }
+  for (int stages : {5, 3}) {
+    P p{};
+    p.w = w; p.rows = 16; p.row_bytes = 2048; p.pitch = 2112; p.stages = stages; p.consume = 1; p.slot_bytes = 16 * 2112; p.sink = sink; p.ksplit = 1;
+    p.bytes_per_cta = (total / ncta) / 32768 * 32768; p.window = 131072;          // 148 x 128 KB = 19 MB working set
+    const int smem = stages * p.slot_bytes + 640;
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0);
+      ring_kernel<<<ncta, 288, smem>>>(p);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    printf("16x2KB, %d stages, L2-RESIDENT source (128 KB window per CTA): %8.1f GB/s = %.1f B/clk/SM at 1.9 GHz (%s)\n", stages,
+           p.bytes_per_cta * ncta / best * 1e-6, p.bytes_per_cta / best * 1e-6 / 1.9, cudaGetErrorString(cudaGetLastError()));
+  }
   // phase-sized bursts: the same ring run for only ~226 KB per CTA (one fc phase), launched back to back
   {
     P p{};
     p.w = w; p.rows = 14; p.row_bytes = 2048; p.pitch = 2112; p.stages = 5; p.consume = 1; p.slot_bytes = 14 * 2112; p.sink = sink; p.ksplit = 1;
     p.bytes_per_cta = 8ull * 14 * 2048;
-    const int smem = 5 * p.slot_bytes + 384;
+    const int smem = 5 * p.slot_bytes + 640;
     cudaEventRecord(e0);
     for (int i = 0; i < 200; ++i) { p.w = w + (unsigned long long)(i % 50) * (40ull << 20); ring_kernel<<<ncta, 288, smem>>>(p); }
     cudaEventRecord(e1); cudaEventSynchronize(e1);

@@ -44,7 +44,7 @@ def _stale(target: str, deps) -> bool:
 # Experimental builds of the same sources (run-time selection: SV_LIB_PATH=<that .so>); never loaded by default.
 VARIANTS = {
     # 4 consumer warps + producer per GEMV CTA, 3 ring slots, two CTAs per SM
-    "nwc4": ["-DSV_NWC=4", "-DSV_STAGES=3", "-DSV_MINBLOCKS=2"],
+    "timeline": ["-DSV_FLOW_TIMELINE=1"],     # dataflow decode kernel with its device timeline records compiled in (scripts/flow_timeline.py)
 }
 
 

@@ -41,9 +41,15 @@ constexpr int FLOW_OFF_BAR = FLOW_OFF_STAT + 2 * NWC * 8 * 4;
 constexpr int FLOW_OFF_TOK = FLOW_OFF_BAR + 2 * STAGES * 8 + 4 * 8;      // + 2 full / 2 empty barriers of the LayerNorm ring
 constexpr int LN_MAX_H = 2 * KS_MAX;          // LayerNorm width the parameter ring holds (the flow kernel needs H <= 2048)
 constexpr int LN_SLOT_BYTES = 2 * LN_MAX_H * 2;                          // weight row + bias row, bf16
+constexpr int FLOW_OFF_PROG = FLOW_OFF_TOK + 48;                         // producer progress counter + "ring full" flag (read by the L2 prefetch warp)
 constexpr int FLOW_OFF_STATE = FLOW_OFF_TOK + 64;                        // CTA 0: GenState + GenParamsDev working copies
 constexpr int FLOW_OFF_LN = (FLOW_OFF_STATE + (int)sizeof(GenState) + (int)sizeof(GenParamsDev) + 127) & ~127;   // [2][LN_SLOT_BYTES]
-constexpr int FLOW_SMEM_BYTES = FLOW_OFF_LN + 2 * LN_SLOT_BYTES + 128;
+// per-layer pointer table and the five tile plans: read on every phase change, so they live in shared memory (as device-memory
+// pointer chasing / integer divisions they cost ~1-2K cycles of the token's critical path per phase)
+constexpr int FLOW_MAX_LAYERS = 24;
+constexpr int FLOW_OFF_LAYERS = FLOW_OFF_LN + 2 * LN_SLOT_BYTES;
+constexpr int FLOW_OFF_PLANS = FLOW_OFF_LAYERS + FLOW_MAX_LAYERS * (int)sizeof(Layer);
+constexpr int FLOW_SMEM_BYTES = FLOW_OFF_PLANS + 5 * (int)sizeof(Plan) + 128;
 static_assert(FLOW_SMEM_BYTES <= 232448, "dataflow decode kernel: shared memory over the 227 KB per-CTA limit");
 
 struct FlowArgs {
@@ -51,6 +57,7 @@ struct FlowArgs {
   int n_layer, B, H, I, n_head, n_kv, qkv_cols, vocab, tcap, n_positions;
   float ln_eps;
   const bf16 *wte, *wpe, *lnf_w, *lnf_b, *lm_head;
+  const bf16* lm_head_t;         // lm_head in the slab-tiled layout (see flow_repack_kernel)
   bf16* x_plain;                 // [B][H] bf16: input of the first step when first_plain; refreshed by every select
   bf16* logits;                  // [B][vocab] bf16 (plain stores; read by the host path / the penalised scan)
   uint32_t *xa, *xb, *qkv, *att, *hb;          // flagged bf16 words: [B][H], [B][H], [B][qkv_cols], [B][H], [B][I]
@@ -88,17 +95,30 @@ SV_DEVINL void st_rlx16B(void* p, uint4 v) {
 }
 SV_DEVINL void spin_guard(uint32_t& it) { if (++it > (1u << 26)) __trap(); }
 
+SV_DEVINL Plan plan_of(const uint8_t* smem, int kind) { return reinterpret_cast<const Plan*>(smem + FLOW_OFF_PLANS)[kind]; }
+
 // phase tags
-SV_DEVINL uint32_t tag16(uint32_t gp) { return ((gp % 65535u) + 1u) << 16; }    // in the upper half of a bf16 word
+SV_DEVINL uint32_t tag16(uint32_t gp) { return ((gp & 0x7fffu) + 1u) << 16; }   // in the upper half of a bf16 word (a stale word is <= 2 phases old)
 SV_DEVINL unsigned long long tag32(uint32_t gp) { return (unsigned long long)(gp + 1u) << 32; }
 SV_DEVINL unsigned long long fword(float v, unsigned long long T) { return T | (unsigned long long)__float_as_uint(v); }
 
+// Layout of a flagged bf16 vector [B][n]: the 8 words of one MMA fragment (32 bytes = one L2 sector) are contiguous,
+// consecutive fragments are FRAG_STRIDE words (256 bytes) apart.  All 148 CTAs poll the same vector at the same moment: packed
+// densely (8 KB for n = 2048) those reads hit 32 L2 slices and one hop took 4.5K cycles; one fragment per 256-byte chunk (the
+// L2 slice hash works on address bits >= 8) spreads them over the whole L2: 3.1K cycles (scripts/hop_latency.cu).
+constexpr int FRAG_STRIDE = 64;
+SV_DEVINL int64_t ll_words(int n) { return (int64_t)(n >> 3) * FRAG_STRIDE; }                       // words per image row
+SV_DEVINL int64_t ll_off(int i) { return (int64_t)(i >> 3) * FRAG_STRIDE + (i & 7); }              // word i of a row
+
+// A poll = ISSUE every load first, CHECK afterwards.  (Checking each fragment right behind its own loads made the `asm
+// volatile` loads issue one L2 round trip after the other: 8 serialised round trips per poll of a GEMV prologue.)
+struct LLRaw { uint4 a, b; };
+SV_DEVINL void ll_issue(const uint32_t* p, LLRaw& r) { r.a = ld_rlx16(p); r.b = ld_rlx16(p + 4); }
 // 8 consecutive bf16 values out of flagged words; nonzero result = at least one word does not carry tag E yet
-SV_DEVINL uint32_t ll_get8(const uint32_t* p, uint32_t E, uint4& out) {
-  const uint4 a = ld_rlx16(p), b = ld_rlx16(p + 4);
-  out.x = __byte_perm(a.x, a.y, 0x5410); out.y = __byte_perm(a.z, a.w, 0x5410);
-  out.z = __byte_perm(b.x, b.y, 0x5410); out.w = __byte_perm(b.z, b.w, 0x5410);
-  return ((a.x ^ E) | (a.y ^ E) | (a.z ^ E) | (a.w ^ E) | (b.x ^ E) | (b.y ^ E) | (b.z ^ E) | (b.w ^ E)) >> 16;
+SV_DEVINL uint32_t ll_finish(const LLRaw& r, uint32_t E, uint4& out) {
+  out.x = __byte_perm(r.a.x, r.a.y, 0x5410); out.y = __byte_perm(r.a.z, r.a.w, 0x5410);
+  out.z = __byte_perm(r.b.x, r.b.y, 0x5410); out.w = __byte_perm(r.b.z, r.b.w, 0x5410);
+  return ((r.a.x ^ E) | (r.a.y ^ E) | (r.a.z ^ E) | (r.a.w ^ E) | (r.b.x ^ E) | (r.b.y ^ E) | (r.b.z ^ E) | (r.b.w ^ E)) >> 16;
 }
 SV_DEVINL void ll_put8(uint32_t* p, uint32_t E, const uint4& v) {
   st_rlx16B(p, make_uint4(E | (v.x & 0xffffu), E | (v.x >> 16), E | (v.y & 0xffffu), E | (v.y >> 16)));
@@ -125,7 +145,14 @@ constexpr int DBG_HALF = 4096;
 SV_DEVINL void stamp_raw(long long* dbg, int& i, int id) {
   if (dbg && i < DBG_HALF) dbg[i++] = (long long)(((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xffffffffffffull));
 }
-SV_DEVINL void stamp(FCtx& cx, int id) { stamp_raw(cx.dbg, cx.dbg_i, id); }
+#ifndef SV_FLOW_TIMELINE
+#define SV_FLOW_TIMELINE 0        // 1: compile the timeline records in (scripts/flow_timeline.py builds that variant library)
+#endif
+SV_DEVINL void stamp(FCtx& cx, int id) {
+#if SV_FLOW_TIMELINE
+  stamp_raw(cx.dbg, cx.dbg_i, id);
+#endif
+}
 
 enum { EPI_LL = 0, EPI_LMHEAD = 2 };
 
@@ -136,7 +163,6 @@ struct LnRing {
   SV_DEVINL void advance() { if (++slot == 2u) { slot = 0; phase ^= 1u; } }
 };
 SV_DEVINL void produce_ln(LnRing& lr, const bf16* ln_w, const bf16* ln_b, int N, int K, int cta, int ncta, int lane) {
-  if (make_plan(N, K, cta, ncta).ntile <= 0) return;          // the consumers skip the phase as well
   if (lane == 0) {
     const uint32_t fb = lr.full0 + 8u * lr.slot, dst = lr.base + lr.slot * LN_SLOT_BYTES;
     mbar_wait(lr.empty0 + 8u * lr.slot, lr.phase ^ 1u);
@@ -150,20 +176,135 @@ SV_DEVINL void produce_ln(LnRing& lr, const bf16* ln_w, const bf16* ln_b, int N,
 // ---- consumer: one GEMV phase  Y[B,N] = epi( LN?(X)[B,K] . W[N,K]^T ) on flagged activations.
 // X: flagged [B][K] carrying tag EX.  res (optional): flagged [B][N], tag ER.  EPI_LL: Y flagged [B][N], tag EY.
 // EPI_LMHEAD: plain bf16 logits + one flagged argmax partial per (tile, image).
+// ---- waiting for a flagged vector without flooding L2.  While a CTA waits for a phase's input, 256 threads re-issuing their
+// polls back to back put ~1 sector request per clock and CTA on L2 -- with most of the 148 CTAs waiting (e.g. for the one or
+// two CTAs that run the attention) that alone saturates L2 and slows exactly the CTAs everybody is waiting for.  So one warp
+// watches 32 fragments spread over the vector, sleeping between looks; only when those carry the tag does every thread poll
+// its own share (which then mostly succeeds at once).
+SV_DEVINL void wait_vector(const FCtx& cx, const uint32_t* __restrict__ V, uint32_t E, int nfrag) {
+  if (cx.warp == 0) {
+    const uint32_t* p = V + (int64_t)((int)(((long long)cx.lane * nfrag) >> 5)) * FRAG_STRIDE;
+    uint32_t it = 0;
+    for (;;) {
+      LLRaw raw;
+      uint4 v;
+      ll_issue(p, raw);
+      const uint32_t bad = ll_finish(raw, E, v);
+      if (!__any_sync(0xffffffffu, bad != 0)) break;
+      __nanosleep(100);
+      spin_guard(it);
+    }
+  }
+  consumer_sync();
+}
+
+// ---- cooperative poll (+ LayerNorm): the consumer threads fetch a flagged [B][n] vector ONCE per CTA into shared memory,
+// one fragment (8 values, two 16-byte loads) per thread and pass, all loads in flight together, then spin on the tags.
+// With LayerNorm (GPTBigCodeBlock ln_1 / ln_2 / ln_f, vendored modeling_gpt_bigcode.py:700,733; fp32 statistics, bf16 output)
+// every thread also normalises the fragments it fetched, so the work is spread over all 256 threads instead of the few
+// lanes that feed the MMA B operand at small batch, and nothing but the staged bf16 vector has to stay in registers.
+// Statistics are reduced per 32-fragment chunk (one warp, one pass) and summed in chunk order: deterministic.
+// Staged rows are xs_pitch(n) bytes apart (+64: the MMA fragment reads of the 8 image rows then hit different banks).
+// Ends with the consumer threads synchronised: the staged vector may be read.
+SV_DEVINL int xs_pitch(int n) { return n * 2 + 64; }
+SV_DEVINL void stage_vector(FCtx& cx, LnRing* lr, const uint32_t* __restrict__ V, uint32_t E, int n, uint8_t* xs, int kind) {
+  const FlowArgs& a = *cx.a;
+  const int fpr = n >> 3, total = a.B * fpr;           // fragments per row / in all (fpr is a multiple of 32)
+  const int tid = threadIdx.x;
+  const int fs = 31 - __clz(fpr);                     // fpr is a power of two (n = 256 .. 2048)
+  auto slot = [&](int f) { return reinterpret_cast<uint4*>(xs + (f >> fs) * xs_pitch(n) + (f & (fpr - 1)) * 16); };
+  wait_vector(cx, V, E, total);
+  // (the fragments live in shared memory between the steps below, each thread re-reads only what it wrote itself)
+#pragma unroll 1
+  for (int f0 = tid; f0 < total; f0 += 4 * NCT) {      // 4 fragments = 8 loads in flight per thread
+    // (indices past the end are clamped: their loads are real, only their stores are dropped -- no partially defined arrays,
+    // which ptxas would put into local memory, and local memory is an L2 round trip here: 227 KB of the SM are shared memory)
+    const int f1 = min(f0 + NCT, total - 1), f2 = min(f0 + 2 * NCT, total - 1), f3 = min(f0 + 3 * NCT, total - 1);
+    LLRaw r0, r1, r2, r3;
+    uint4 v0, v1, v2, v3;
+    uint32_t bad, it = 0;
+    do {
+      ll_issue(V + (int64_t)f0 * FRAG_STRIDE, r0);       // row b's fragments follow row b - 1's
+      ll_issue(V + (int64_t)f1 * FRAG_STRIDE, r1);
+      ll_issue(V + (int64_t)f2 * FRAG_STRIDE, r2);
+      ll_issue(V + (int64_t)f3 * FRAG_STRIDE, r3);
+      bad = ll_finish(r0, E, v0) | ll_finish(r1, E, v1) | ll_finish(r2, E, v2) | ll_finish(r3, E, v3);
+      if (bad) { __nanosleep(40); spin_guard(it); }
+    } while (bad);
+    *slot(f0) = v0;
+    if (f0 + NCT < total) *slot(f1) = v1;
+    if (f0 + 2 * NCT < total) *slot(f2) = v2;
+    if (f0 + 3 * NCT < total) *slot(f3) = v3;
+  }
+  stamp(cx, 8 * kind + ST_XREADY);
+  if (lr != nullptr) {
+    float* stat = cx.stat;                              // [2][64]: per-chunk sums, then per-chunk centred squares
+    const int cpr = fpr >> 5;                           // 32-fragment chunks per row
+#pragma unroll 1
+    for (int f = tid; f < total; f += NCT) {            // warp-uniform trip count: total is a multiple of 32
+      float fv[8];
+      unpack8(*slot(f), fv);
+      float sum = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += fv[e];
+      sum = warp_sum(sum);
+      if (cx.lane == 0) stat[f >> 5] = sum;
+    }
+    consumer_sync();
+#pragma unroll 1
+    for (int f = tid; f < total; f += NCT) {
+      const int c0 = (f >> fs) * cpr;
+      float m = 0.f;
+      for (int c = 0; c < cpr; ++c) m += stat[c0 + c];
+      const float mean = m / (float)n;
+      float fv[8];
+      unpack8(*slot(f), fv);
+      float q = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float dlt = fv[e] - mean; q += dlt * dlt; }
+      q = warp_sum(q);
+      if (cx.lane == 0) stat[64 + (f >> 5)] = q;
+    }
+    consumer_sync();
+    mbar_wait(lr->full0 + 8u * lr->slot, lr->phase);    // (weight, bias) rows staged by the producer warp, normally long ago
+    const uint32_t lnw = lr->base + lr->slot * LN_SLOT_BYTES, lnb = lnw + LN_MAX_H * 2;
+#pragma unroll 1
+    for (int f = tid; f < total; f += NCT) {
+      const int c0 = (f >> fs) * cpr, fr = f & (fpr - 1);
+      float m = 0.f, var = 0.f;
+      for (int c = 0; c < cpr; ++c) { m += stat[c0 + c]; var += stat[64 + c0 + c]; }
+      const float mean = m / (float)n, rstd = 1.0f / sqrtf(var / (float)n + a.ln_eps);
+      float fv[8], wf[8], bfv[8];
+      unpack8(*slot(f), fv);
+      unpack8(lds16(lnw + fr * 16), wf);
+      unpack8(lds16(lnb + fr * 16), bfv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) fv[e] = (fv[e] - mean) * rstd * wf[e] + bfv[e];
+      *slot(f) = pack8(fv);                              // the LayerNorm output is a bf16 tensor in the reference
+    }
+    __syncwarp();
+    if (cx.lane == 0) mbar_arrive(lr->empty0 + 8u * lr->slot);
+    lr->advance();
+  }
+  consumer_sync();
+  if (lr != nullptr) stamp(cx, 8 * kind + ST_LN);
+}
+
 // has_ln / epi are run-time (warp-uniform) switches on purpose: the kernel holds ONE copy of this code for its five call
 // patterns (a 256 KB kernel thrashed the instruction cache at every phase change).
 SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const int epi, const uint32_t* __restrict__ X, uint32_t EX,
                          const bf16* __restrict__ bias, const uint32_t* res, uint32_t ER, uint32_t* Y, uint32_t EY, int N, int K, int act,
                          uint32_t gp, int kind) {
   const FlowArgs& a = *cx.a;
-  const Plan p = make_plan(N, K, cx.cta, cx.ncta);
+  const Plan p = plan_of(cx.smem, kind);
   if (p.ntile <= 0) return;
   stamp(cx, 8 * kind + ST_ENTER);                          // nothing to do here: go and wait where this CTA has work
   const int warp = cx.warp, g = cx.g, t = cx.t;
   const int cps = p.KS >> 5;                         // 32-wide chunks per slot row
   const int cpws = (cps + NWC - 1) / NWC;            // chunks per warp per slot (<= CPW)
   const bool row_ok = g < a.B;
-  const uint32_t* xp = X + (int64_t)(row_ok ? g : 0) * K + 8 * t;
+  const uint32_t* xp = X + (int64_t)(row_ok ? g : 0) * ll_words(K) + (int64_t)t * FRAG_STRIDE;   // fragment t of chunk 0
+  constexpr int CHUNK = 4 * FRAG_STRIDE;             // words between the fragments of consecutive 32-wide k chunks
   const bool big_k = p.nstg > 2;
 
   // activations of the whole phase live in registers when K <= 2048 (8 fragments per lane)
@@ -171,81 +312,15 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
 #pragma unroll
   for (int i = 0; i < 2 * CPW; ++i) xr[i] = make_uint4(0u, 0u, 0u, 0u);
   if (!big_k) {
+    uint8_t* xs = cx.smem + OFF_ATT;                   // the attention scratch is free during a GEMV phase
+    stage_vector(cx, has_ln ? &lr : nullptr, X, EX, K, xs, kind);
     if (row_ok) {
-      uint32_t bad, it = 0;
-      do {
-        bad = 0;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
+      for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-          for (int j = 0; j < CPW; ++j) {
-            const int cl = warp + NWC * j;
-            if (ks < p.nstg && j < cpws && cl < cps) bad |= ll_get8(xp + (ks * cps + cl) * 32, EX, xr[ks * CPW + j]);
-          }
-        }
-        if (bad) spin_guard(it);
-      } while (bad);
-    }
-    stamp(cx, 8 * kind + ST_XREADY);
-    if (has_ln) {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 2 * CPW; ++i) {
-        float f[8];
-        unpack8(xr[i], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += f[j];
-      }
-      s = quad_sum(s);
-      if (t == 0) cx.stat[warp * 8 + g] = s;
-      consumer_sync();
-      float mean = 0.f;
-#pragma unroll
-      for (int w = 0; w < NWC; ++w) mean += cx.stat[w * 8 + g];
-      mean /= (float)K;
-      float q = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-        for (int j = 0; j < CPW; ++j) {
-          const bool okc = ks < p.nstg && j < cpws && (warp + NWC * j) < cps;
-          if (okc) {
-            float f[8];
-            unpack8(xr[ks * CPW + j], f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { const float dlt = f[e] - mean; q += dlt * dlt; }
-          }
-        }
-      }
-      q = quad_sum(q);
-      if (t == 0) cx.stat[NWC * 8 + warp * 8 + g] = q;       // second half of stat[]: no write-after-read barrier needed
-      consumer_sync();
-      float var = 0.f;
-#pragma unroll
-      for (int w = 0; w < NWC; ++w) var += cx.stat[NWC * 8 + w * 8 + g];
-      const float rstd = 1.0f / sqrtf(var / (float)K + a.ln_eps);
-      mbar_wait(lr.full0 + 8u * lr.slot, lr.phase);          // staged by the producer warp, normally long ago
-      const uint32_t lnw = lr.base + lr.slot * LN_SLOT_BYTES + 16 * t, lnb = lnw + LN_MAX_H * 2;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-        for (int j = 0; j < CPW; ++j) {
-          const int cl = warp + NWC * j;
-          const bool okc = ks < p.nstg && j < cpws && cl < cps;
-          float f[8], wf[8], bfv[8];
-          unpack8(xr[ks * CPW + j], f);
-          const int ch = okc ? ks * cps + cl : 0;
-          unpack8(lds16(lnw + ch * 64), wf);
-          unpack8(lds16(lnb + ch * 64), bfv);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = (row_ok && okc) ? (f[e] - mean) * rstd * wf[e] + bfv[e] : 0.f;
-          xr[ks * CPW + j] = pack8(f);       // ln output is a bf16 tensor in the reference; 0 on padded chunks
-        }
-      }
-      __syncwarp();
-      if (cx.lane == 0) mbar_arrive(lr.empty0 + 8u * lr.slot);
-      lr.advance();
-      stamp(cx, 8 * kind + ST_LN);
+        for (int j = 0; j < CPW; ++j)
+          if (ks < p.nstg && j < cpws && (warp + NWC * j) < cps)
+            xr[ks * CPW + j] = *reinterpret_cast<const uint4*>(xs + g * xs_pitch(K) + ((ks * cps + warp + NWC * j) * 4 + t) * 16);
     }
   }
 
@@ -257,9 +332,8 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
     const int ecol = tile * p.R + en;
     const bool eok = threadIdx.x < 128 && en < p.R && ecol < N && emm < a.B;
     uint32_t rword = 0;
-    if (res != nullptr && eok) rword = ld_rlx32(res + (int64_t)emm * N + ecol);
-    float bias_v = 0.f;                                  // fetched now: an HBM miss here must not sit behind the last MMA
-    if (bias != nullptr && eok) bias_v = __bfloat162float(bias[ecol]);
+    if (res != nullptr && eok) rword = ld_rlx32(res + emm * ll_words(N) + ll_off(ecol));
+    float bias_v = 0.f;                                  // read from the padding of the tile's last slab (flow_repack_kernel)
     if (!big_k) {
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
@@ -277,6 +351,8 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
               mma_bf16_16816(c, lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
             }
           }
+          if (bias != nullptr && ks == p.nstg - 1 && threadIdx.x < 128)
+            bias_v = __uint_as_float(*reinterpret_cast<const uint32_t*>(cx.smem + r.slot * SLOT_BYTES + en * p.pitch + p.KS * 2) << 16);
           __syncwarp();
           if (cx.lane == 0) mbar_arrive(r.empty0 + 8u * r.slot);
           r.advance();
@@ -292,7 +368,7 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
         for (int j = 0; j < CPW; ++j) {
           const int cl = warp + NWC * j;
           if (row_ok && ks < p.nstg && j < cpws && cl < cps) {
-            const uint32_t* q = xp + (ks * cps + cl) * 32;
+            const uint32_t* q = xp + (int64_t)(ks * cps + cl) * CHUNK;
             ra[j] = ld_rlx16(q); rb[j] = ld_rlx16(q + 4);
           }
         }
@@ -315,6 +391,7 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
               }
             }
             if (!bad) break;
+            __nanosleep(40);
             spin_guard(it);
             issue(ks);
           }
@@ -339,6 +416,8 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
             mma_bf16_16816(c, lo.z, hi.z, lo.w, hi.w, xc[j].z, xc[j].w);
           }
         }
+        if (bias != nullptr && ks == p.nstg - 1 && threadIdx.x < 128)
+          bias_v = __uint_as_float(*reinterpret_cast<const uint32_t*>(cx.smem + r.slot * SLOT_BYTES + en * p.pitch + p.KS * 2) << 16);
         __syncwarp();
         if (cx.lane == 0) mbar_arrive(r.empty0 + 8u * r.slot);
         r.advance();
@@ -362,13 +441,13 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
         float rv = 0.f;
         if (res != nullptr) {
           uint32_t it = 0;
-          while ((rword ^ ER) >> 16) { spin_guard(it); rword = ld_rlx32(res + (int64_t)emm * N + ecol); }
+          while ((rword ^ ER) >> 16) { spin_guard(it); rword = ld_rlx32(res + emm * ll_words(N) + ll_off(ecol)); }
           rv = __uint_as_float(rword << 16);
         }
         v = epilogue_elem(acc, bv, act, res != nullptr, rv);
         const bf16 vb = __float2bfloat16_rn(v);
         if (epi == EPI_LL) {
-          st_rlx32(Y + (int64_t)emm * N + ecol, EY | (uint32_t)__bfloat16_as_ushort(vb));
+          st_rlx32(Y + emm * ll_words(N) + ll_off(ecol), EY | (uint32_t)__bfloat16_as_ushort(vb));
         } else {
           a.logits[(int64_t)emm * N + ecol] = vb;
         }
@@ -410,11 +489,13 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
 // One item covers <= 16 key blocks (512 keys).  Up to 512 keys of context a single item holds the whole row: it
 // normalises and writes the attention output directly (no merge hop).  Longer rows are cut into items of <= 8 blocks
 // whose (m, l, acc) partials go to merge_flow as flagged fp32 words.
-constexpr int ATT_R = 2;                                  // key blocks per warp and item
+constexpr int ATT_R = 1;                                  // key blocks per warp and item (2: a warp's blocks run one after the other)
 constexpr int ATT_BLKS = NWC * ATT_R;                     // key blocks per item
 constexpr int ATT_P_BYTES = ATT_BLKS * 2 * 32 * 16;       // P fragments: [block][h][lane] x 16 bytes
-constexpr int OFF_ATT_M = OFF_ATT + ATT_P_BYTES;          // float [NWC][16] row maxima, then [NWC][16] row sums
-static_assert(ATT_P_BYTES + 2 * NWC * 16 * 4 <= ATT_BYTES, "attention scratch must fit the mega layout's tree-merge buffer");
+constexpr int OFF_ATT_M = OFF_ATT + ATT_P_BYTES;          // float [ATT_BLKS][16] block row maxima, then [ATT_BLKS][16] block row sums
+constexpr int OFF_ATT_Q = OFF_ATT_M + 2 * ATT_BLKS * 16 * 4;   // the item's query heads, bf16 [16][D]
+static_assert(ATT_P_BYTES + 2 * ATT_BLKS * 16 * 4 + 16 * D * 2 + 2 * D * 2 <= ATT_BYTES, "attention scratch must fit the mega layout's tree-merge buffer");
+static_assert(8 * (2 * KS_MAX * 2 + 64) <= ATT_BYTES, "the staged activation vector (8 rows x 2048 values) shares that buffer");
 
 SV_DEVINL void attn_split(int nkeys, int& nact, int& per) {
   const int nblk = (nkeys + 31) / 32;
@@ -425,20 +506,33 @@ SV_DEVINL void attn_split(int nkeys, int& nact, int& per) {
 }
 
 // S (log2 domain, scaled, masked) of one 32-key block: thread (g, t) gets keys kb + 8t + 2j + e for head rows g (s[j][e])
-// and g + 8 (s[j][2 + e]) -- the layout the P.V A operand needs (sv_attention.cu, fragment trick).
-SV_DEVINL void qk_block(const uint32_t (&qa)[D / 16][4], const bf16* __restrict__ kbase, int kb, int key_end, float scale_log2,
-                        float (&s)[4][4], int g, int t) {
+// and g + 8 (s[j][2 + e]) -- the layout the P.V A operand needs (sv_attention.cu, fragment trick).  The row of key `cur_key`
+// (the token being decoded: not in the cache yet) is read from shared memory at `ks` instead.
+SV_DEVINL void qk_block(const uint32_t (&qa)[D / 16][4], const bf16* __restrict__ kbase, int kb, int key_end, int cur_key, uint32_t ks,
+                        float scale_log2, float (&s)[4][4], int g, int t) {
+  // all 16 K fragments of the lane are requested before the first MMA (one L2 round trip for the block, not sixteen);
+  // the current token's row is fetched from global like any other (valid memory, stale content) and replaced by a select
+  uint4 w[4][D / 32];
+  bool cur[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int key = kb + 8 * (g >> 1) + 2 * j + (g & 1);
+    key = key < key_end ? key : key_end - 1;
+    cur[j] = key == cur_key;
+    const bf16* kp = kbase + (int64_t)key * D + 8 * t;
+#pragma unroll
+    for (int jj = 0; jj < D / 32; ++jj) w[j][jj] = ldcg16(kp + 32 * jj);
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-    int key = kb + 8 * (g >> 1) + 2 * j + (g & 1);
-    key = key < key_end ? key : key_end - 1;
-    const bf16* kp = kbase + (int64_t)key * D + 8 * t;
 #pragma unroll
     for (int jj = 0; jj < D / 32; ++jj) {
-      const uint4 w = ldcg16(kp + 32 * jj);
-      mma_bf16_16816(s[j], qa[2 * jj][0], qa[2 * jj][1], qa[2 * jj][2], qa[2 * jj][3], w.x, w.y);
-      mma_bf16_16816(s[j], qa[2 * jj + 1][0], qa[2 * jj + 1][1], qa[2 * jj + 1][2], qa[2 * jj + 1][3], w.z, w.w);
+      const uint4 c = lds16(ks + (32 * jj + 8 * t) * 2);
+      uint4 v = w[j][jj];
+      v.x = cur[j] ? c.x : v.x; v.y = cur[j] ? c.y : v.y; v.z = cur[j] ? c.z : v.z; v.w = cur[j] ? c.w : v.w;
+      mma_bf16_16816(s[j], qa[2 * jj][0], qa[2 * jj][1], qa[2 * jj][2], qa[2 * jj][3], v.x, v.y);
+      mma_bf16_16816(s[j], qa[2 * jj + 1][0], qa[2 * jj + 1][1], qa[2 * jj + 1][2], qa[2 * jj + 1][3], v.z, v.w);
     }
   }
 #pragma unroll
@@ -452,6 +546,16 @@ SV_DEVINL void qk_block(const uint32_t (&qa)[D / 16][4], const bf16* __restrict_
   }
 }
 
+// 8 keys of one V^T row (what the P.V B operand of a lane holds for a block): the element of key index `e` (0..7) is replaced
+// by `val` -- the current token's v, which is not in the cache yet.  Written with selects only (no register indexing).
+SV_DEVINL void patch_v(uint4& w, int e, uint32_t val) {
+  const uint32_t lo = (e & 1) ? 0x0000ffffu : 0xffff0000u, ins = (e & 1) ? (val << 16) : val;
+  w.x = (e >> 1) == 0 ? ((w.x & lo) | ins) : w.x;
+  w.y = (e >> 1) == 1 ? ((w.y & lo) | ins) : w.y;
+  w.z = (e >> 1) == 2 ? ((w.z & lo) | ins) : w.z;
+  w.w = (e >> 1) == 3 ? ((w.w & lo) | ins) : w.w;
+}
+
 SV_DEVINL void attention_flow(FCtx& cx, const Layer* L, int cur_len, uint32_t E, uint32_t gp) {
   const FlowArgs& a = *cx.a;
   const int warp = cx.warp, lane = cx.lane, g = cx.g, t = cx.t;
@@ -463,162 +567,155 @@ SV_DEVINL void attention_flow(FCtx& cx, const Layer* L, int cur_len, uint32_t E,
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   const uint32_t pbuf = smem_u32(cx.smem + OFF_ATT);
   float* mbuf = reinterpret_cast<float*>(cx.smem + OFF_ATT_M);
-  float* lbuf = mbuf + NWC * 16;
+  float* lbuf = mbuf + ATT_BLKS * 16;
+  uint8_t* qs = cx.smem + OFF_ATT_Q;                       // staged: the group's query heads [16][D], then k_cur [D], v_cur [D]
+  const uint32_t ks = smem_u32(qs + 16 * D * 2);
+  const unsigned short* vs = reinterpret_cast<const unsigned short*>(qs + 16 * D * 2 + D * 2);
   const unsigned long long T = tag32(gp);
   const int nitems = a.B * a.n_kv * nact;
   stamp(cx, ST_ATT_ENTER);
   for (int item = cx.cta; item < nitems; item += cx.ncta) {
     const int c = item % nact, bk = item / nact, kvh = bk % a.n_kv, b = bk / a.n_kv;
     const int blk0 = c * per, blk1 = min(nblk, blk0 + per), nb = blk1 - blk0;
+    const bool has_cur = blk1 == nblk;                     // this item's last block holds the token being decoded
+    const int cur_key = has_cur ? cur_len : -1;
     bf16* kb_ = L->kc + (int64_t)bk * a.tcap * D;
     bf16* vb_ = L->vc + (int64_t)bk * D * a.tcap;
-    const uint32_t* qkv_row = a.qkv + (int64_t)b * a.qkv_cols;
-    // ---- sub-phase 1: scores of this warp's key blocks
-    float s[ATT_R][4][4];
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-    if (warp < nb) {
-      const uint32_t* qrow = qkv_row + (int64_t)kvh * group * D;
-      uint32_t qa[D / 16][4];
-      {
-        uint4 lo[D / 32], hi[D / 32];
-#pragma unroll
-        for (int jj = 0; jj < D / 32; ++jj) { lo[jj] = make_uint4(0u, 0u, 0u, 0u); hi[jj] = make_uint4(0u, 0u, 0u, 0u); }
-        uint32_t bad, it = 0;
-        do {
-          bad = 0;
-#pragma unroll
-          for (int jj = 0; jj < D / 32; ++jj) {
-            if (g < group) bad |= ll_get8(qrow + (int64_t)g * D + 32 * jj + 8 * t, E, lo[jj]);
-            if (g + 8 < group) bad |= ll_get8(qrow + (int64_t)(g + 8) * D + 32 * jj + 8 * t, E, hi[jj]);
-          }
-          if (bad) spin_guard(it);
-        } while (bad);
-#pragma unroll
-        for (int jj = 0; jj < D / 32; ++jj) {
-          qa[2 * jj][0] = lo[jj].x; qa[2 * jj][1] = hi[jj].x; qa[2 * jj][2] = lo[jj].y; qa[2 * jj][3] = hi[jj].y;
-          qa[2 * jj + 1][0] = lo[jj].z; qa[2 * jj + 1][1] = hi[jj].z; qa[2 * jj + 1][2] = lo[jj].w; qa[2 * jj + 1][3] = hi[jj].w;
+    const uint32_t* qkv_row = a.qkv + b * ll_words(a.qkv_cols);
+    // ---- one cooperative poll: the group's query heads and (last item only) the current token's k, v -> shared memory.
+    // The cache append itself happens after the math: the current key / value are used from shared memory
+    // (GPTBigCodeAttention.forward: key_value = cat(layer_past, key_value), vendored modeling_gpt_bigcode.py:265-267).
+    {
+      const int nq = group * (D / 8), nfr = nq + (has_cur ? 2 * (D / 8) : 0);
+      wait_vector(cx, qkv_row + (int64_t)(kvh * nq) * FRAG_STRIDE, E, nq);
+      for (int f0 = threadIdx.x; f0 < nfr; f0 += NCT) {
+        const int frag = f0 < nq ? kvh * nq + f0
+                                 : (f0 < nq + D / 8 ? (a.n_head + kvh) * (D / 8) + (f0 - nq) : (a.n_head + a.n_kv + kvh) * (D / 8) + (f0 - nq - D / 8));
+        LLRaw raw;
+        uint4 v;
+        uint32_t it = 0;
+        for (;;) {
+          ll_issue(qkv_row + (int64_t)frag * FRAG_STRIDE, raw);
+          if (!ll_finish(raw, E, v)) break;
+          __nanosleep(40);
+          spin_guard(it);
         }
+        *reinterpret_cast<uint4*>(qs + (f0 < nq ? f0 : 16 * (D / 8) + (f0 - nq)) * 16) = v;
       }
-      stamp(cx, ST_ATT_Q);
-      // the warp that reads the newest key block appends the current token's k / v to the cache first
-      // (GPTBigCodeAttention.forward: key_value = cat(layer_past, key_value), vendored modeling_gpt_bigcode.py:265-267);
-      // the other warps read that V^T column only after the CTA barrier below
-      if (blk1 == nblk && ((nb - 1) % NWC) == warp && cur_len < a.tcap) {
-        const uint32_t* kll = qkv_row + (int64_t)a.n_head * D + (int64_t)kvh * D + 4 * lane;
-        const uint32_t* vll = kll + (int64_t)a.n_kv * D;
-        uint4 kw, vw;
-        uint32_t bad, it = 0;
-        do {
-          kw = ld_rlx16(kll); vw = ld_rlx16(vll);
-          bad = ((kw.x ^ E) | (kw.y ^ E) | (kw.z ^ E) | (kw.w ^ E) | (vw.x ^ E) | (vw.y ^ E) | (vw.z ^ E) | (vw.w ^ E)) >> 16;
-          if (bad) spin_guard(it);
-        } while (bad);
-        uint2 kp;
-        kp.x = __byte_perm(kw.x, kw.y, 0x5410); kp.y = __byte_perm(kw.z, kw.w, 0x5410);
-        __stcg(reinterpret_cast<uint2*>(kb_ + (int64_t)cur_len * D + 4 * lane), kp);
-        unsigned short* vt = reinterpret_cast<unsigned short*>(vb_) + (int64_t)(4 * lane) * a.tcap + cur_len;
-        __stcg(vt, (unsigned short)(vw.x & 0xffffu));
-        __stcg(vt + a.tcap, (unsigned short)(vw.y & 0xffffu));
-        __stcg(vt + 2 * (int64_t)a.tcap, (unsigned short)(vw.z & 0xffffu));
-        __stcg(vt + 3 * (int64_t)a.tcap, (unsigned short)(vw.w & 0xffffu));
-        __threadfence_block();
-        __syncwarp();
-      }
+      consumer_sync();
+    }
+    stamp(cx, ST_ATT_Q);
+    // ---- V^T loads of every key block of the item: issued now, used after the scores (they only depend on addresses)
+    const bf16* v0 = vb_ + (int64_t)(16 * warp + g) * a.tcap + blk0 * 32 + 8 * t;       // V^T row of n-tile 0; n-tile 1: + 8 rows
+    uint4 vv[ATT_BLKS][2];
 #pragma unroll
+    for (int i = 0; i < ATT_BLKS / 2; ++i) {               // first half now, second half once the K fragments are consumed
+      const int bi = min(i, nb - 1);
+      vv[i][0] = ldcg16(v0 + bi * 32);
+      vv[i][1] = ldcg16(v0 + 8 * (int64_t)a.tcap + bi * 32);
+    }
+    // ---- sub-phase 1: scores of this warp's key blocks.  Every block is finished on the spot with ITS OWN row maxima
+    // (P = exp2(S - m_block), bf16, parked as MMA A fragments; m_block and the row sums go to shared memory): no score outlives
+    // its block, the item-wide maximum enters later as one scale factor per (block, head) on the block's P.V product.
+    if (warp < nb) {
+      uint32_t qa[D / 16][4];
+#pragma unroll
+      for (int jj = 0; jj < D / 32; ++jj) {
+        uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
+        if (g < group) lo = *reinterpret_cast<const uint4*>(qs + (g * (D / 8) + 4 * jj + t) * 16);
+        if (g + 8 < group) hi = *reinterpret_cast<const uint4*>(qs + ((g + 8) * (D / 8) + 4 * jj + t) * 16);
+        qa[2 * jj][0] = lo.x; qa[2 * jj][1] = hi.x; qa[2 * jj][2] = lo.y; qa[2 * jj][3] = hi.y;
+        qa[2 * jj + 1][0] = lo.z; qa[2 * jj + 1][1] = hi.z; qa[2 * jj + 1][2] = lo.w; qa[2 * jj + 1][3] = hi.w;
+      }
+#pragma unroll 1
       for (int r = 0; r < ATT_R; ++r) {
         const int bi = warp + r * NWC;
         if (bi < nb) {
           const int kb = (blk0 + bi) * 32;
-          qk_block(qa, kb_, kb, min(nkeys, kb + 32), scale_log2, s[r], g, t);
+          float s[4][4];
+          qk_block(qa, kb_, kb, min(nkeys, kb + 32), cur_key, ks, scale_log2, s, g, t);
+          float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            mx0 = fmaxf(mx0, fmaxf(s[r][j][0], s[r][j][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[r][j][2], s[r][j][3]));
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
           }
-        }
-      }
-      mx0 = quad_max(mx0); mx1 = quad_max(mx1);
-    }
-    if (t == 0) { mbuf[warp * 16 + g] = mx0; mbuf[warp * 16 + g + 8] = mx1; }
-    consumer_sync();
-    stamp(cx, ST_ATT_BLK);
-    // ---- item-wide row maxima, P = exp2(S - M) parked as MMA A fragments, row sums
-    float M0 = -INFINITY, M1 = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < NWC; ++w) { M0 = fmaxf(M0, mbuf[w * 16 + g]); M1 = fmaxf(M1, mbuf[w * 16 + g + 8]); }
-    float rs0 = 0.f, rs1 = 0.f;
-    if (warp < nb) {
-#pragma unroll
-      for (int r = 0; r < ATT_R; ++r) {
-        const int bi = warp + r * NWC;
-        if (bi < nb) {
+          mx0 = quad_max(mx0); mx1 = quad_max(mx1);           // finite: a block always holds at least one real key
+          float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            s[r][j][0] = exp2f(s[r][j][0] - M0); s[r][j][1] = exp2f(s[r][j][1] - M0);
-            s[r][j][2] = exp2f(s[r][j][2] - M1); s[r][j][3] = exp2f(s[r][j][3] - M1);
-            rs0 += s[r][j][0] + s[r][j][1]; rs1 += s[r][j][2] + s[r][j][3];
+            s[j][0] = exp2f(s[j][0] - mx0); s[j][1] = exp2f(s[j][1] - mx0);
+            s[j][2] = exp2f(s[j][2] - mx1); s[j][3] = exp2f(s[j][3] - mx1);
+            rs0 += s[j][0] + s[j][1]; rs1 += s[j][2] + s[j][3];
           }
+          rs0 = quad_sum(rs0); rs1 = quad_sum(rs1);
+          if (t == 0) { mbuf[bi * 16 + g] = mx0; mbuf[bi * 16 + g + 8] = mx1; lbuf[bi * 16 + g] = rs0; lbuf[bi * 16 + g + 8] = rs1; }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint4 pa;
-            pa.x = pack_bf16x2(s[r][2 * h][0], s[r][2 * h][1]);
-            pa.y = pack_bf16x2(s[r][2 * h][2], s[r][2 * h][3]);
-            pa.z = pack_bf16x2(s[r][2 * h + 1][0], s[r][2 * h + 1][1]);
-            pa.w = pack_bf16x2(s[r][2 * h + 1][2], s[r][2 * h + 1][3]);
+            pa.x = pack_bf16x2(s[2 * h][0], s[2 * h][1]);
+            pa.y = pack_bf16x2(s[2 * h][2], s[2 * h][3]);
+            pa.z = pack_bf16x2(s[2 * h + 1][0], s[2 * h + 1][1]);
+            pa.w = pack_bf16x2(s[2 * h + 1][2], s[2 * h + 1][3]);
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pbuf + ((bi * 2 + h) * 32 + lane) * 16), "r"(pa.x), "r"(pa.y),
                          "r"(pa.z), "r"(pa.w) : "memory");
           }
         }
       }
     }
-    rs0 = quad_sum(rs0); rs1 = quad_sum(rs1);
-    if (t == 0) { lbuf[warp * 16 + g] = rs0; lbuf[warp * 16 + g + 8] = rs1; }
+#pragma unroll
+    for (int i = ATT_BLKS / 2; i < ATT_BLKS; ++i) {
+      const int bi = min(i, nb - 1);
+      vv[i][0] = ldcg16(v0 + bi * 32);
+      vv[i][1] = ldcg16(v0 + 8 * (int64_t)a.tcap + bi * 32);
+    }
     consumer_sync();
-    // ---- sub-phase 2: out[:, 16 * warp + {0..15}] = P . V over every key block of the item
-    float acc[2][4];
+    stamp(cx, ST_ATT_BLK);
+    // ---- sub-phase 2: out[:, 16 * warp + {0..15}] = sum over the item's key blocks of 2^(m_block - M) * P_block . V_block
+    float M0 = -INFINITY, M1 = -INFINITY;
+    for (int bi = 0; bi < nb; ++bi) { M0 = fmaxf(M0, mbuf[bi * 16 + g]); M1 = fmaxf(M1, mbuf[bi * 16 + g + 8]); }
+    float acc[2][4], L0 = 0.f, L1 = 0.f;
 #pragma unroll
     for (int n = 0; n < 2; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-    const bf16* v0 = vb_ + (int64_t)(16 * warp + g) * a.tcap + blk0 * 32 + 8 * t;       // V^T row of n-tile 0; n-tile 1: + 8 rows
-#pragma unroll 1
-    for (int b0 = 0; b0 < nb; b0 += 4) {
-      uint4 vv[4][2];
+    // the lane whose 8 keys of the last block contain the current token takes its v from shared memory
+    const int cur_e = cur_len - (nblk - 1) * 32 - 8 * t;       // element index inside that lane's 8 keys, if in [0, 8)
+    const bool patch = has_cur && cur_e >= 0 && cur_e < 8;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (b0 + i < nb) {
-          vv[i][0] = ldcg16(v0 + (b0 + i) * 32);
-          vv[i][1] = ldcg16(v0 + 8 * (int64_t)a.tcap + (b0 + i) * 32);
+    for (int bi = 0; bi < ATT_BLKS; ++bi) {
+      if (bi < nb) {
+        if (patch && bi == nb - 1) {
+          patch_v(vv[bi][0], cur_e, (uint32_t)vs[16 * warp + g]);
+          patch_v(vv[bi][1], cur_e, (uint32_t)vs[16 * warp + 8 + g]);
         }
-      }
+        const uint4 p0 = lds16(pbuf + ((bi * 2 + 0) * 32 + lane) * 16), p1 = lds16(pbuf + ((bi * 2 + 1) * 32 + lane) * 16);
+        const float sc0 = exp2f(mbuf[bi * 16 + g] - M0), sc1 = exp2f(mbuf[bi * 16 + g + 8] - M1);
+        L0 += lbuf[bi * 16 + g] * sc0; L1 += lbuf[bi * 16 + g + 8] * sc1;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (b0 + i < nb) {
-          const uint4 p0 = lds16(pbuf + (((b0 + i) * 2 + 0) * 32 + lane) * 16), p1 = lds16(pbuf + (((b0 + i) * 2 + 1) * 32 + lane) * 16);
-#pragma unroll
-          for (int n = 0; n < 2; ++n) {
-            mma_bf16_16816(acc[n], p0.x, p0.y, p0.z, p0.w, vv[i][n].x, vv[i][n].y);
-            mma_bf16_16816(acc[n], p1.x, p1.y, p1.z, p1.w, vv[i][n].z, vv[i][n].w);
-          }
+        for (int n = 0; n < 2; ++n) {
+          float pv[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_16816(pv, p0.x, p0.y, p0.z, p0.w, vv[bi][n].x, vv[bi][n].y);
+          mma_bf16_16816(pv, p1.x, p1.y, p1.z, p1.w, vv[bi][n].z, vv[bi][n].w);
+          acc[n][0] += pv[0] * sc0; acc[n][1] += pv[1] * sc0; acc[n][2] += pv[2] * sc1; acc[n][3] += pv[3] * sc1;
         }
       }
     }
-    float L0 = 0.f, L1 = 0.f;
-#pragma unroll
-    for (int w = 0; w < NWC; ++w) { L0 += lbuf[w * 16 + g]; L1 += lbuf[w * 16 + g + 8]; }
     stamp(cx, ST_ATT_TREE);
     if (nact == 1) {
       // the whole row was in this item: normalise and publish the attention output (bf16, like the reference's attn_output)
-      uint32_t* orow = a.att + (int64_t)b * a.n_head * D + (int64_t)kvh * group * D;
+      uint32_t* orow = a.att + b * ll_words(a.n_head * D);
       const float i0 = 1.0f / L0, i1 = 1.0f / L1;
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
-        const int d = 16 * warp + 8 * n + 2 * t;
+        const int d = 16 * warp + 8 * n + 2 * t;           // d, d + 1 share a fragment
         if (g < group) {
-          st_rlx32(orow + g * D + d, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][0] * i0)));
-          st_rlx32(orow + g * D + d + 1, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][1] * i0)));
+          uint32_t* o = orow + ll_off((kvh * group + g) * D + d);
+          st_rlx32(o, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][0] * i0)));
+          st_rlx32(o + 1, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][1] * i0)));
         }
         if (g + 8 < group) {
-          st_rlx32(orow + (g + 8) * D + d, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][2] * i1)));
-          st_rlx32(orow + (g + 8) * D + d + 1, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][3] * i1)));
+          uint32_t* o = orow + ll_off((kvh * group + g + 8) * D + d);
+          st_rlx32(o, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][2] * i1)));
+          st_rlx32(o + 1, E | (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[n][3] * i1)));
         }
       }
     } else {
@@ -635,6 +732,13 @@ SV_DEVINL void attention_flow(FCtx& cx, const Layer* L, int cur_len, uint32_t E,
       }
     }
     stamp(cx, ST_ATT_DONE);
+    // ---- the cache append, off the critical path: K row (16 x 16 bytes) and V^T column (D x 2 bytes) from the staged copies
+    if (has_cur && cur_len < a.tcap) {
+      const int tid = threadIdx.x;
+      if (tid < D / 8) __stcg(reinterpret_cast<uint4*>(kb_ + (int64_t)cur_len * D) + tid, *reinterpret_cast<const uint4*>(qs + 16 * D * 2 + tid * 16));
+      if (tid >= 32 && tid < 32 + D)
+        __stcg(reinterpret_cast<unsigned short*>(vb_) + (int64_t)(tid - 32) * a.tcap + cur_len, vs[tid - 32]);
+    }
     consumer_sync();                                      // the scratch is reused by the CTA's next item
   }
 }
@@ -658,16 +762,19 @@ SV_DEVINL void merge_flow(FCtx& cx, int cur_len, uint32_t E, uint32_t gp) {
       uint32_t it = 0;
       bool bad;
       do {
-        bad = false;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8; ++j) {                    // every load of the poll first ...
           if (c0 + j < nact) {
             const unsigned long long* pc = p0 + (int64_t)(c0 + j) * PSZ;
             wm[j] = ld_rlx64(pc + rr); wl[j] = ld_rlx64(pc + 16 + rr); wa[j] = ld_rlx64(pc + 32 + rr * D + dim);
-            bad |= ((wm[j] ^ T) >> 32) != 0 || ((wl[j] ^ T) >> 32) != 0 || ((wa[j] ^ T) >> 32) != 0;
           }
         }
-        if (bad) spin_guard(it);
+        unsigned long long x = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)                      // ... then the tags
+          if (c0 + j < nact) x |= (wm[j] ^ T) | (wl[j] ^ T) | (wa[j] ^ T);
+        bad = (x >> 32) != 0;
+        if (bad) { __nanosleep(100); spin_guard(it); }
       } while (bad);
       float Mn = M;
 #pragma unroll
@@ -685,7 +792,7 @@ SV_DEVINL void merge_flow(FCtx& cx, int cur_len, uint32_t E, uint32_t gp) {
       }
     }
     const bf16 o = __float2bfloat16_rn(A / Lsum);
-    st_rlx32(a.att + (int64_t)b * a.n_head * D + head * D + dim, E | (uint32_t)__bfloat16_as_ushort(o));
+    st_rlx32(a.att + b * ll_words(a.n_head * D) + ll_off(head * D + dim), E | (uint32_t)__bfloat16_as_ushort(o));
   }
 }
 
@@ -706,7 +813,7 @@ SV_DEVINL void embed_flow(const FCtx& cx, const int* toks, int pos, uint32_t E) 
       for (int j = 0; j < 8; ++j) e[j] += q[j];
     }
     const uint4 v = pack8(e);
-    ll_put8(a.xa + (int64_t)b * a.H + col, E, v);
+    ll_put8(a.xa + b * ll_words(a.H) + ll_off(col), E, v);
     *reinterpret_cast<uint4*>(a.x_plain + (int64_t)b * a.H + col) = v;
   }
 }
@@ -730,13 +837,14 @@ SV_DEVINL void select_flow(FCtx& cx, int ntiles, uint32_t gp, int next_pos, uint
       uint32_t it = 0;
       bool bad;
       do {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (i0 + j * NCT < ntiles) w[j] = ld_rlx64(a.amax + (int64_t)(i0 + j * NCT) * 8 + b);
         bad = false;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = i0 + j * NCT;
-          if (i < ntiles) { w[j] = ld_rlx64(a.amax + (int64_t)i * 8 + b); bad |= (uint32_t)(w[j] >> 48) != T16; }
-        }
-        if (bad) spin_guard(it);
+        for (int j = 0; j < 4; ++j)
+          if (i0 + j * NCT < ntiles) bad |= (uint32_t)(w[j] >> 48) != T16;
+        if (bad) { __nanosleep(100); spin_guard(it); }
       } while (bad);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -782,58 +890,43 @@ SV_DEVINL void select_flow(FCtx& cx, int ntiles, uint32_t gp, int next_pos, uint
 
 // ---- the static schedule: phase q of a token = layer q / 4, kind q % 4 (0 c_attn, 1 attn.c_proj, 2 mlp.c_fc, 3 mlp.c_proj);
 // q == 4 * n_layer is the lm_head
-struct PhaseW { const bf16 *W, *ln_w, *ln_b; int N, K, kind; };
-SV_DEVINL PhaseW phase_weights(const FlowArgs& a, int q) {
+struct PhaseW { const bf16 *W, *ln_w, *ln_b; int N, K, kind; };     // W: the slab-tiled copy of the phase's weight matrix
+SV_DEVINL PhaseW phase_weights(const FlowArgs& a, const Layer* layers, int q) {
   PhaseW w;
   w.ln_w = nullptr; w.ln_b = nullptr;
-  if (q == 4 * a.n_layer) { w.W = a.lm_head; w.N = a.vocab; w.K = a.H; w.kind = 4; w.ln_w = a.lnf_w; w.ln_b = a.lnf_b; return w; }
-  const Layer* L = a.layers + (q >> 2);
+  if (q == 4 * a.n_layer) { w.W = a.lm_head_t; w.N = a.vocab; w.K = a.H; w.kind = 4; w.ln_w = a.lnf_w; w.ln_b = a.lnf_b; return w; }
+  const Layer* L = layers + (q >> 2);
   w.kind = q & 3;
   switch (w.kind) {
-    case 0: w.W = L->attn_w; w.N = a.qkv_cols; w.K = a.H; w.ln_w = L->ln1_w; w.ln_b = L->ln1_b; break;
-    case 1: w.W = L->proj_w; w.N = a.H; w.K = a.H; break;
-    case 2: w.W = L->fc_w; w.N = a.I; w.K = a.H; w.ln_w = L->ln2_w; w.ln_b = L->ln2_b; break;
-    default: w.W = L->fc2_w; w.N = a.H; w.K = a.I; break;
+    case 0: w.W = L->attn_t; w.N = a.qkv_cols; w.K = a.H; w.ln_w = L->ln1_w; w.ln_b = L->ln1_b; break;
+    case 1: w.W = L->proj_t; w.N = a.H; w.K = a.H; break;
+    case 2: w.W = L->fc_t; w.N = a.I; w.K = a.H; w.ln_w = L->ln2_w; w.ln_b = L->ln2_b; break;
+    default: w.W = L->fc2_t; w.N = a.H; w.K = a.I; break;
   }
   return w;
 }
 
-// Position of one CTA in the weight schedule of the launch: (token, phase, tile, k slab).  The producer warp keeps two
-// of them: `cur` feeds the shared-memory ring, `pf` runs `l2_ahead` slabs further and only asks L2 to fetch
-// (cp.async.bulk.prefetch.L2), so that HBM keeps streaming while the ring is full and the consumers sit in a
-// latency-bound phase (attention, hops): the ring then refills from L2 at L2 speed.
-struct WeightWalk {
-  int s, q, tl, ks, cta, ncta;
-  bool done;
-  PhaseW w;
-  Plan p;
-  SV_DEVINL void load(const FlowArgs& a) {
-    for (;;) {
-      if (s >= a.nsteps) { done = true; return; }
-      w = phase_weights(a, q);
-      p = make_plan(w.N, w.K, cta, ncta);
-      if (p.ntile > 0) return;
-      if (++q > 4 * a.n_layer) { q = 0; ++s; }
+// L2 prefetch that works (scripts/l2_prefetch_test.cu): one 4-byte ld.global.cg with the L2::128B prefetch size per 128-byte
+// line.  `rows` pieces of `row_bytes` (a multiple of 128), `row_stride` bytes apart; one warp, 8 independent loads per lane in
+// flight.  The loaded words are folded into `t.acc` only at the NEXT call (by then they have long arrived): that keeps the
+// eight destination registers distinct and alive -- dead outputs would share one register and serialise on its scoreboard --
+// without ever waiting for a load that was just issued.
+struct L2Touch { uint32_t v[8], acc; };
+SV_DEVINL void l2_touch(L2Touch& t, const char* base, int rows, int64_t row_stride, int row_bytes, int lane) {
+  const int lpr = row_bytes >> 7, nlines = rows * lpr;
+  for (int i0 = lane; i0 < nlines; i0 += 8 * 32) {
+    t.acc ^= t.v[0] ^ t.v[1] ^ t.v[2] ^ t.v[3] ^ t.v[4] ^ t.v[5] ^ t.v[6] ^ t.v[7];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = min(i0 + k * 32, nlines - 1);
+      asm volatile("ld.global.cg.L2::128B.u32 %0, [%1];" : "=r"(t.v[k]) : "l"(base + (int64_t)(i / lpr) * row_stride + (i % lpr) * 128) : "memory");
     }
   }
-  SV_DEVINL void init(const FlowArgs& a, int cta_, int ncta_) { s = 0; q = 0; tl = 0; ks = 0; cta = cta_; ncta = ncta_; done = false; load(a); }
-  SV_DEVINL bool at_phase_start() const { return tl == 0 && ks == 0; }
-  SV_DEVINL void next(const FlowArgs& a) {
-    if (++ks < p.nstg) return;
-    ks = 0;
-    if (++tl < p.ntile) return;
-    tl = 0;
-    if (++q > 4 * a.n_layer) { q = 0; ++s; }
-    load(a);
-  }
-  SV_DEVINL const bf16* row_ptr(int lane) const { return w.W + (int64_t)((p.tile0 + tl) * p.R + lane) * w.K + (int64_t)ks * p.KS; }
-  SV_DEVINL int rows() const { return min(p.R, w.N - (p.tile0 + tl) * p.R); }
-};
+}
 
-// The producer also asks L2 for the K / V^T blocks this CTA's attention items of layer l will read (everything but the
-// current token, which arrives as flagged words): issued when the ring starts on the layer's c_attn weights, i.e. a few
-// microseconds before the attention phase, so its dependent loads hit L2 instead of HBM.
-SV_DEVINL void prefetch_kv_l2(const FlowArgs& a, const Layer* L, int cur_len, int cta, int ncta, int lane) {
+// The prefetch warp also pulls the K / V^T blocks this CTA's attention items of a layer will read (everything but the current
+// token, which arrives as flagged words) into L2 a few microseconds before the attention phase.
+SV_DEVINL void prefetch_kv_l2(L2Touch& tch, const FlowArgs& a, const Layer* L, int cur_len, int cta, int ncta, int lane) {
   if (cur_len <= 0) return;
   const int nkeys = cur_len + 1, nblk = (nkeys + 31) / 32;
   int nact, per;
@@ -843,21 +936,18 @@ SV_DEVINL void prefetch_kv_l2(const FlowArgs& a, const Layer* L, int cur_len, in
     const int c = item % nact, bk = item / nact;
     const int key0 = c * per * 32, key1 = min(cur_len, min(nblk, c * per + per) * 32);       // cached keys of the item
     if (key1 <= key0) continue;
-    const char* kp = reinterpret_cast<const char*>(L->kc + ((int64_t)bk * a.tcap + key0) * D);
-    const int kbytes = (key1 - key0) * D * 2, piece = ((kbytes + 31) / 32 + 15) & ~15;
-    if (lane * piece < kbytes)
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kp + lane * piece), "r"((uint32_t)min(piece, kbytes - lane * piece)) : "memory");
-    const int vbytes = ((key1 - key0) * 2 + 15) & ~15;
-#pragma unroll
-    for (int r = 0; r < D / 32; ++r) {
-      const char* vp = reinterpret_cast<const char*>(L->vc + ((int64_t)bk * D + lane + 32 * r) * a.tcap + key0);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vp), "r"((uint32_t)vbytes) : "memory");
-    }
+    const int kbytes = ((key1 - key0) * D * 2 + 127) & ~127;                                 // K rows are contiguous
+    l2_touch(tch, reinterpret_cast<const char*>(L->kc + ((int64_t)bk * a.tcap + key0) * D), 1, 0, kbytes, lane);
+    const int vbytes = ((key1 - key0) * 2 + 127) & ~127;                                     // V^T: D rows, tcap * 2 bytes apart
+    l2_touch(tch, reinterpret_cast<const char*>(L->vc + (int64_t)bk * D * a.tcap + key0), D, (int64_t)a.tcap * 2, vbytes, lane);
   }
 }
 
+constexpr int FLOW_THREADS = NCT + 64;        // 8 consumer warps + producer warp + L2 prefetch warp
+constexpr int FLOW_THREADS_REALLOC = NCT + 128;
+
 template <bool REALLOC>
-__global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow_kernel(const FlowArgs a) {
+__global__ void __launch_bounds__(REALLOC ? FLOW_THREADS_REALLOC : FLOW_THREADS, 1) decode_flow_kernel(const FlowArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -873,47 +963,108 @@ __global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow
   lnr.empty0 = lnr.full0 + 16u;
   lnr.slot = 0; lnr.phase = 0;
   if (threadIdx.x == 0) {
+    *reinterpret_cast<uint32_t*>(smem + FLOW_OFF_PROG) = 0u;
+    *reinterpret_cast<uint32_t*>(smem + FLOW_OFF_PROG + 4) = 0u;
     for (int s = 0; s < STAGES; ++s) { mbar_init(ring.full0 + 8u * s, 1); mbar_init(ring.empty0 + 8u * s, NWC); }
     for (int s = 0; s < 2; ++s) { mbar_init(lnr.full0 + 8u * s, 1); mbar_init(lnr.empty0 + 8u * s, NWC); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const Layer* layers_s = reinterpret_cast<const Layer*>(smem + FLOW_OFF_LAYERS);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.layers);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + FLOW_OFF_LAYERS);
+    for (int i = threadIdx.x; i < a.n_layer * (int)(sizeof(Layer) / 4); i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 5) {
+      const int k = threadIdx.x;
+      const int N = k == 0 ? a.qkv_cols : (k == 2 ? a.I : (k == 4 ? a.vocab : a.H)), K = k == 3 ? a.I : a.H;
+      reinterpret_cast<Plan*>(smem + FLOW_OFF_PLANS)[k] = make_plan(N, K, cta, ncta);
+    }
   }
   __syncthreads();
 
   if (warp >= NWC) {
     if constexpr (REALLOC) {
+      // the pool is what the launch allocated (384 x 168): the 4 x 32 x (168 - 56) registers given back here are exactly the
+      // 8 x 32 x (224 - 168) the consumers ask for below -- any other split never gets its setmaxnreg.inc satisfied
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
-      if (warp > NWC) return;
+      if (warp > NWC + 1) return;
     }
-    // =========================== producer: the static weight schedule of the whole launch ===========================
-    long long* pdbg = (a.dbg != nullptr && cta == 0 && lane == 0) ? a.dbg + DBG_HALF : nullptr;
-    int pi = 0;
-    WeightWalk cur, pf;
-    cur.init(a, cta, ncta);
-    pf.init(a, cta, ncta);
-    auto prefetch_slab = [&]() {
-      if (lane < pf.rows())
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.row_ptr(lane)), "r"((uint32_t)(pf.p.KS * 2)) : "memory");
-      pf.next(a);
-    };
-    for (int i = 0; i < a.l2_ahead && !pf.done; ++i) prefetch_slab();
-    while (!cur.done) {
-      if (a.l2_ahead > 0 && !pf.done) prefetch_slab();
-      if (cur.at_phase_start()) {
-        if (cur.s > 0) pdbg = nullptr;
-        stamp_raw(pdbg, pi, ST_PROD + 2 * cur.w.kind);
-        if (cur.w.ln_w != nullptr) produce_ln(lnr, cur.w.ln_w, cur.w.ln_b, cur.w.N, cur.w.K, cta, ncta, lane);
-        if (cur.w.kind == 0 && a.l2_ahead > 0) prefetch_kv_l2(a, a.layers + (cur.q >> 2), a.cur_len0 + cur.s, cta, ncta, lane);
+    const uint32_t progress = smem_u32(smem + FLOW_OFF_PROG);                                   // slabs the producer has issued
+    if (warp == NWC) {
+      // =========================== producer: the static weight schedule of the whole launch ===========================
+      // Plain nested loops (token, phase, tile, k slab): per slab only the wait for a free slot and <= 16 bulk copies,
+      // one per lane -- this loop must stay far ahead of the consumers (an earlier version that re-derived its position
+      // from a generic iterator for every slab fell behind them and halved the throughput).
+      long long* pdbg = (a.dbg != nullptr && cta == 0 && lane == 0) ? a.dbg + DBG_HALF : nullptr;
+      int pi = 0;
+      uint32_t issued = 0;
+      for (int s = 0; s < a.nsteps; ++s) {
+        if (s == 1) pdbg = nullptr;
+        for (int q = 0; q <= 4 * a.n_layer; ++q) {
+          const PhaseW w = phase_weights(a, layers_s, q);
+          const Plan p = plan_of(smem, w.kind);
+          if (p.ntile <= 0) continue;                                    // the consumers skip the phase as well
+          stamp_raw(pdbg, pi, ST_PROD + 2 * w.kind);
+          if (w.ln_w != nullptr) produce_ln(lnr, w.ln_w, w.ln_b, w.N, w.K, cta, ncta, lane);
+          // the CTA's slabs of this matrix are one contiguous run of SLOT_BYTES blocks in the tiled copy (flow_repack_kernel):
+          // ONE bulk copy per slab (a 2 KB copy per weight row topped out at 19.5 B/clk/SM even from L2, one 30 KB copy
+          // reaches 36.8: scripts/ring_stream.cu)
+          const char* src = reinterpret_cast<const char*>(w.W) + (int64_t)cta * p.tpc * p.nstg * SLOT_BYTES;
+          const uint32_t bytes = (uint32_t)(p.R * p.pitch);
+          const int nslab = p.ntile * p.nstg;
+          for (int i = 0; i < nslab; ++i) {
+            if (lane == 0) {
+              const uint32_t fb = ring.full0 + 8u * ring.slot;
+              // "blocked" = the ring is full and the consumers are not draining it (a latency-bound stretch): only then does
+              // the prefetch warp run ahead -- its requests would otherwise queue in front of the slabs the ring is waiting for
+              asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(progress + 4u), "r"(1u) : "memory");
+              mbar_wait(ring.empty0 + 8u * ring.slot, ring.phase ^ 1u);
+              asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(progress + 4u), "r"(0u) : "memory");
+              mbar_expect_tx(fb, bytes);
+              bulk_g2s(ring.base + ring.slot * SLOT_BYTES, src + (int64_t)i * SLOT_BYTES, bytes, fb);
+              asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(progress), "r"(++issued) : "memory");
+            }
+            ring.advance();
+          }
+        }
       }
-      const uint32_t fb = ring.full0 + 8u * ring.slot;
-      const int rows = cur.rows();
-      if (lane == 0) {
-        mbar_wait(ring.empty0 + 8u * ring.slot, ring.phase ^ 1u);
-        mbar_expect_tx(fb, (uint32_t)(rows * cur.p.KS * 2));
+    } else {
+      // =========================== L2 prefetcher: the same schedule, `l2_ahead` slabs in front of the producer ==========
+      // cp.async.bulk.prefetch.L2 only: HBM keeps streaming into L2 while the ring is full and the consumers sit in a
+      // latency-bound stretch (attention, hops); the ring then refills from L2.
+      uint32_t j = 0;
+      L2Touch tch;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tch.v[k] = 0u;
+      tch.acc = 0u;
+      for (int s = 0; s < a.nsteps; ++s) {
+        for (int q = 0; q <= 4 * a.n_layer; ++q) {
+          const PhaseW w = phase_weights(a, layers_s, q);
+          const Plan p = plan_of(smem, w.kind);
+          const char* src = reinterpret_cast<const char*>(w.W) + (int64_t)cta * p.tpc * p.nstg * SLOT_BYTES;
+          const int nslab = p.ntile * p.nstg, bytes = (p.R * p.pitch + 127) & ~127;
+          for (int i = 0; i < nslab; ++i, ++j) {
+            uint32_t it = 0, prog, blocked;
+            for (;;) {
+              asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(prog) : "r"(progress) : "memory");
+              asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(blocked) : "r"(progress + 4u) : "memory");
+              if ((int32_t)(j - prog) < STAGES) break;                        // fell behind the ring: skip ahead
+              if ((int32_t)(j - prog) <= a.l2_ahead && blocked) break;
+              __nanosleep(100);
+              spin_guard(it);
+            }
+            if (a.l2_ahead > 0 && (int32_t)(j - prog) >= STAGES)              // slabs the ring is about to copy need no hint
+              l2_touch(tch, src + (int64_t)i * SLOT_BYTES, 1, 0, bytes, lane);
+          }
+          // K / V of the NEXT attention phase: while the schedule is in mlp.c_proj of the layer before (or the lm_head of the
+          // previous token), i.e. roughly one phase ahead of the c_attn GEMV whose output the attention waits for
+          if (w.kind == 3 && (q >> 2) + 1 < a.n_layer) prefetch_kv_l2(tch, a, layers_s + (q >> 2) + 1, a.cur_len0 + s, cta, ncta, lane);
+          if (w.kind == 4 && s + 1 < a.nsteps) prefetch_kv_l2(tch, a, layers_s, a.cur_len0 + s + 1, cta, ncta, lane);
+        }
       }
-      __syncwarp();
-      if (lane < rows) bulk_g2s(ring.base + ring.slot * SLOT_BYTES + lane * cur.p.pitch, cur.row_ptr(lane), (uint32_t)(cur.p.KS * 2), fb);
-      ring.advance();
-      cur.next(a);
+      // (never true: the fold only exists to keep the prefetch loads' registers alive)
+      if ((tch.acc ^ tch.v[0] ^ tch.v[1] ^ tch.v[2] ^ tch.v[3] ^ tch.v[4] ^ tch.v[5] ^ tch.v[6] ^ tch.v[7]) == 0x9e3779b9u && a.nsteps < 0)
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(progress), "r"(tch.acc) : "memory");
     }
     return;   // in-flight bulk copies are all consumed (and thus complete) before the consumers exit
   }
@@ -934,7 +1085,7 @@ __global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow
     for (int i = threadIdx.x; i < n0 + n1; i += NCT) dst[i] = i < n0 ? s0[i] : s1[i - n0];
     consumer_sync();
   }
-  const int ntiles_lm = make_plan(a.vocab, a.H, 0, ncta).ntiles;
+  const int ntiles_lm = plan_of(smem, 4).ntiles;
   const uint32_t nl1 = (uint32_t)a.n_layer + 1u;
   if (a.first_plain && cta == 0) {
     // the step-0 input was written as plain bf16 by the kernel that selected / embedded the previous token
@@ -942,7 +1093,7 @@ __global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow
     const int hv = a.H >> 3;
     for (int i = threadIdx.x; i < a.B * hv; i += NCT) {
       const int b = i / hv, col = (i % hv) * 8;
-      ll_put8(a.xa + (int64_t)b * a.H + col, E0, __ldcg(reinterpret_cast<const uint4*>(a.x_plain + (int64_t)b * a.H + col)));
+      ll_put8(a.xa + b * ll_words(a.H) + ll_off(col), E0, __ldcg(reinterpret_cast<const uint4*>(a.x_plain + (int64_t)b * a.H + col)));
     }
   }
   for (int s = 0; s < a.nsteps; ++s) {
@@ -953,8 +1104,8 @@ __global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow
       const int l = q >> 2;
       const uint32_t gp = gs * nl1 + (uint32_t)l;          // the lm_head (q = 4 * n_layer) is "layer n_layer"
       const uint32_t E = tag16(gp), En = tag16(gp + 1u);
-      const PhaseW w = phase_weights(a, q);
-      const Layer* L = a.layers + (l < a.n_layer ? l : 0);
+      const PhaseW w = phase_weights(a, layers_s, q);
+      const Layer* L = layers_s + (l < a.n_layer ? l : 0);
       const uint32_t *X, *res = nullptr;
       uint32_t *Y = nullptr, EY = E;
       const bf16* bias = nullptr;
@@ -981,7 +1132,47 @@ __global__ void __launch_bounds__(REALLOC ? NCT + 128 : NTHREADS, 1) decode_flow
   }
 }
 
+// ---- slab-tiled copy of a decode weight matrix W [N][K] and its bias (made once, when the weights are loaded): for CTA c, tile t, k slab s
+// the block ((c * tpc + t) * nstg + s) * SLOT_BYTES holds the R rows x KS columns of that slab with the shared-memory row pitch
+// (KS * 2 + 64 bytes) already applied, rows beyond N and the padding zeroed -- exactly the bytes of one ring slot, so the
+// producer moves a slab with a single bulk copy and a CTA's whole share of the matrix is one linear range.
+__global__ void __launch_bounds__(256) flow_repack_kernel(const bf16* __restrict__ W, const bf16* __restrict__ bias, uint8_t* __restrict__ T, int N,
+                                                          int K, int ncta) {
+  const Plan p = make_plan(N, K, blockIdx.x, ncta);
+  const int tl = blockIdx.y / p.nstg, ks = blockIdx.y % p.nstg;
+  if (blockIdx.y >= p.tpc * p.nstg) return;
+  uint8_t* dst = T + ((int64_t)(blockIdx.x * p.tpc + tl) * p.nstg + ks) * SLOT_BYTES;
+  const int row0 = (p.tile0 + tl) * p.R;
+  const int vec_per_row = p.pitch / 16;                                   // 16-byte vectors per padded row
+  for (int i = threadIdx.x; i < 16 * vec_per_row; i += 256) {
+    const int r = i / vec_per_row, v = i % vec_per_row;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (tl < p.ntile && r < p.R && row0 + r < N && v * 8 < p.KS)
+      val = *reinterpret_cast<const uint4*>(W + (int64_t)(row0 + r) * K + (int64_t)ks * p.KS + v * 8);
+    // the first two bytes of a row's 64-byte padding carry that output row's bias: the epilogue thread takes it from the slab
+    // it has just multiplied (a separate global load sat behind ~20 MB of queued weight traffic and stalled the ring)
+    if (bias != nullptr && tl < p.ntile && r < p.R && row0 + r < N && v * 8 == p.KS)
+      val.x = (uint32_t)__bfloat16_as_ushort(bias[row0 + r]);
+    if (i * 16 < SLOT_BYTES) *reinterpret_cast<uint4*>(dst + (int64_t)i * 16) = val;
+  }
+}
+
 }  // namespace flow
+
+size_t flow_tiled_bytes(int N, int K, int ncta) {
+  const int rows_per_cta = (N + ncta - 1) / ncta, tpc = (rows_per_cta + 15) / 16;
+  int ks = 32;
+  for (int c : {1024, 768, 512, 256, 128, 64}) if (c <= K && K % c == 0) { ks = c; break; }
+  return (size_t)ncta * tpc * (K / ks) * mega::SLOT_BYTES;
+}
+
+void launch_flow_repack(const bf16* W, const bf16* bias, void* T, int N, int K, int ncta, cudaStream_t st) {
+  const int rows_per_cta = (N + ncta - 1) / ncta, tpc = (rows_per_cta + 15) / 16;
+  int ks = 32;
+  for (int c : {1024, 768, 512, 256, 128, 64}) if (c <= K && K % c == 0) { ks = c; break; }
+  flow::flow_repack_kernel<<<dim3(ncta, tpc * (K / ks)), 256, 0, st>>>(W, bias, reinterpret_cast<uint8_t*>(T), N, K, ncta);
+  count_launch();
+}
 
 // ---- host side
 static int g_flow_ncta = 0;
@@ -999,9 +1190,9 @@ cudaError_t decode_flow_init() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow::decode_flow_kernel<false>, mega::NTHREADS, flow::FLOW_SMEM_BYTES);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow::decode_flow_kernel<false>, flow::FLOW_THREADS, flow::FLOW_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  if (!realloc_attr_ok || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_realloc, flow::decode_flow_kernel<true>, mega::NCT + 128,
+  if (!realloc_attr_ok || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_realloc, flow::decode_flow_kernel<true>, flow::FLOW_THREADS_REALLOC,
                                                                          flow::FLOW_SMEM_BYTES) != cudaSuccess) {
     per_sm_realloc = 0;
     cudaGetLastError();
@@ -1009,7 +1200,7 @@ cudaError_t decode_flow_init() {
   g_flow_ncta = (coop && per_sm >= 1) ? nsm : 0;
   g_flow_realloc_ok = coop && per_sm_realloc >= 1;
   snprintf(g_flow_why, sizeof(g_flow_why), "sms=%d coop=%d blocks_per_sm=%d (setmaxnreg variant: %d) smem=%d threads=%d -> ncta=%d", nsm,
-           coop, per_sm, per_sm_realloc, flow::FLOW_SMEM_BYTES, mega::NTHREADS, g_flow_ncta);
+           coop, per_sm, per_sm_realloc, flow::FLOW_SMEM_BYTES, flow::FLOW_THREADS, g_flow_ncta);
   return cudaSuccess;
 }
 bool decode_flow_realloc_supported() { return g_flow_realloc_ok; }
@@ -1019,7 +1210,7 @@ int decode_flow_partial_floats() { return mega::PSZ; }
 bool decode_flow_supported(int H, int I, int head_dim, int max_batch, int window, bool rope) {
   auto okk = [](int K) { return K % 32 == 0 && (K <= mega::KS_MAX ? true : K % mega::KS_MAX == 0); };
   return mega::NWC == 8 && g_flow_ncta > 0 && head_dim == mega::D && okk(H) && okk(I) && H <= 2 * mega::KS_MAX && max_batch <= 8 &&
-         window == 0 && !rope;
+         window == 0 && !rope;      // (+ n_layer <= FLOW_MAX_LAYERS, checked at launch)
 }
 
 cudaError_t launch_decode_flow(const FlowLaunch& m, cudaStream_t st) {
@@ -1027,20 +1218,21 @@ cudaError_t launch_decode_flow(const FlowLaunch& m, cudaStream_t st) {
   a.layers = reinterpret_cast<const mega::Layer*>(m.layers_dev);
   a.n_layer = m.n_layer; a.B = m.B; a.H = m.H; a.I = m.I; a.n_head = m.n_head; a.n_kv = m.n_kv; a.qkv_cols = m.qkv_cols;
   a.vocab = m.vocab; a.tcap = m.tcap; a.n_positions = m.n_positions; a.ln_eps = m.ln_eps;
-  a.wte = m.wte; a.wpe = m.wpe; a.lnf_w = m.lnf_w; a.lnf_b = m.lnf_b; a.lm_head = m.lm_head;
+  a.wte = m.wte; a.wpe = m.wpe; a.lnf_w = m.lnf_w; a.lnf_b = m.lnf_b; a.lm_head = m.lm_head; a.lm_head_t = m.lm_head_t;
   a.x_plain = m.x_plain; a.logits = m.logits;
   a.xa = m.xa; a.xb = m.xb; a.qkv = m.qkv; a.att = m.att; a.hb = m.hb; a.part = m.part; a.amax = m.amax;
   a.state = m.state; a.params = m.params; a.seen = m.seen; a.next_ids = m.next_ids; a.out_ids = m.out_ids;
   a.nsteps = m.nsteps; a.step0 = m.step0; a.cur_len0 = m.cur_len0; a.first_plain = m.first_plain; a.do_select = m.do_select;
   a.l2_ahead = m.l2_ahead;
   a.dbg = m.dbg;
+  if (m.n_layer > flow::FLOW_MAX_LAYERS) return cudaErrorInvalidValue;
   void* args[] = {&a};
   cudaError_t e;
   if (m.realloc)
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(flow::decode_flow_kernel<true>), dim3(g_flow_ncta), dim3(mega::NCT + 128), args,
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(flow::decode_flow_kernel<true>), dim3(g_flow_ncta), dim3(flow::FLOW_THREADS_REALLOC), args,
                                     flow::FLOW_SMEM_BYTES, st);
   else
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(flow::decode_flow_kernel<false>), dim3(g_flow_ncta), dim3(mega::NTHREADS), args,
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(flow::decode_flow_kernel<false>), dim3(g_flow_ncta), dim3(flow::FLOW_THREADS), args,
                                     flow::FLOW_SMEM_BYTES, st);
   count_launch();
   return e;

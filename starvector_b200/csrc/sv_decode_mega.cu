@@ -61,6 +61,10 @@ struct Ctx {
   int cta, ncta, warp, lane, g, t;
   float* red;     // [2][NWC][16][8]
   float* stat;    // [NWC][8]
+  // optional (per-phase ring kernels): parameters staged into shared memory BEFORE the programmatic-dependency wait, so that
+  // their HBM misses overlap the previous kernel's tail instead of sitting on this kernel's critical path
+  uint32_t ln_s = 0;            // shared address of [ln_w row | ln_b row] (K bf16 each), 0 = read them from global
+  const float* bias_s = nullptr;   // [tile][16] biases of this CTA's output rows
 };
 
 // ---- consumer: one GEMV phase  Y[B,N] = epi( LN?(X)[B,K] . W[N,K]^T )
@@ -141,8 +145,13 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
           float f[8], wf[8], bfv[8];
           unpack8(xr[ks * CPW + j], f);
           const int ch = okc ? ks * cps + cl : 0;
-          unpack8(ldg_cached(ln_w + ch * 32 + 8 * t), wf);
-          unpack8(ldg_cached(ln_b + ch * 32 + 8 * t), bfv);
+          if (cx.ln_s) {
+            unpack8(lds16(cx.ln_s + (ch * 32 + 8 * t) * 2), wf);
+            unpack8(lds16(cx.ln_s + (K + ch * 32 + 8 * t) * 2), bfv);
+          } else {
+            unpack8(ldg_cached(ln_w + ch * 32 + 8 * t), wf);
+            unpack8(ldg_cached(ln_b + ch * 32 + 8 * t), bfv);
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = (row_ok && okc) ? (f[e] - mean) * rstd * wf[e] + bfv[e] : 0.f;
           xr[ks * CPW + j] = pack8(f);       // ln output is a bf16 tensor in the reference; 0 on padded chunks
@@ -200,8 +209,16 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
   }
 
   float c[4] = {0.f, 0.f, 0.f, 0.f};
+  int pos_now = 0;
+  if constexpr (EPI == EPI_QKV) pos_now = __ldcg(&a.state->cur_len);         // read here, not behind the last MMA
   for (int tl = 0; tl < p.ntile; ++tl) {
     const int tile = p.tile0 + tl;
+    // the epilogue thread's residual value: requested now, used after the MMAs (an L2 round trip off the tail)
+    float res_pre = 0.f;
+    {
+      const int n_ = threadIdx.x & 15, mm_ = threadIdx.x >> 4, col_ = tile * p.R + n_;
+      if (res != nullptr && threadIdx.x < 128 && n_ < p.R && col_ < N && mm_ < a.B) res_pre = __bfloat162float(__ldcg(res + (int64_t)mm_ * N + col_));
+    }
     if (!big_k) {
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
@@ -292,15 +309,14 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
       const bool ok = n < p.R && col < N && mm < a.B;
       float v = 0.f;
       if (ok) {
-        const float bv = bias ? __bfloat162float(bias[col]) : 0.f;
-        float rv = 0.f;
-        if (res) rv = __bfloat162float(__ldcg(res + (int64_t)mm * N + col));
+        const float bv = bias ? (cx.bias_s ? cx.bias_s[tl * 16 + n] : __bfloat162float(bias[col])) : 0.f;
+        const float rv = res_pre;
         v = epilogue_elem(acc, bv, act, res != nullptr, rv);
         const bf16 vb = __float2bfloat16_rn(v);
         Y[(int64_t)mm * N + col] = vb;
         if constexpr (EPI == EPI_QKV) {
           const int q_cols = a.n_head * D, j = col - q_cols;
-          const int pos = __ldcg(&a.state->cur_len);
+          const int pos = pos_now;
           if (j >= 0 && pos < a.tcap) {
             if (j < a.n_kv * D) {
               const int kvh = j / D, dim = j % D;
@@ -581,7 +597,10 @@ SV_DEVINL void l2_prefetch_share(const void* base, unsigned long long bytes, int
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"((uint32_t)n) : "memory");
   }
 }
-SV_DEVINL constexpr int ring_smem_bytes(int nslots) { return nslots * SLOT_BYTES + RED_BYTES + NWC * 8 * 4 + 2 * 8 * 8 + 256; }
+constexpr int RING_BIAS_TILES = 8;     // biases staged for up to this many tiles per CTA (mlp.c_fc has 4)
+SV_DEVINL constexpr int ring_smem_bytes(int nslots) {
+  return nslots * SLOT_BYTES + RED_BYTES + NWC * 8 * 4 + 2 * 8 * 8 + 16 + 2 * 2 * KS_MAX * 2 + RING_BIAS_TILES * 16 * 4 + 256;
+}
 
 // (A 2-CTA/SM register budget (96 regs) so that consecutive kernels co-reside under PDL was measured 25% slower.)
 template <bool HAS_LN, int EPI, bool LN_BIGK = false>
@@ -607,11 +626,33 @@ __global__ void __launch_bounds__(NTHREADS, RING_MINBLOCKS) gemv_ring_kernel(con
     l2_prefetch_share(ra.next_w, ra.next_bytes, cta, ncta, lane);
     return;
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   Ctx cx;
   cx.a = &ra.a; cx.smem = smem; cx.cta = cta; cx.ncta = ncta; cx.warp = warp; cx.lane = lane; cx.g = lane >> 2; cx.t = lane & 3;
   cx.red = reinterpret_cast<float*>(smem + off_red);
   cx.stat = reinterpret_cast<float*>(smem + off_stat);
+  // immutable parameters (LayerNorm affine, biases of this CTA's rows) are staged into shared memory before the wait on the
+  // previous kernel: their HBM misses (~1 us each, two per LayerNorm kernel, one per epilogue) overlap that kernel's tail
+  {
+    const int off_par = (off_bar + 2 * 8 * 8 + 15) & ~15;
+    if (HAS_LN && !LN_BIGK && ra.K <= 2 * KS_MAX) {
+      cx.ln_s = smem_u32(smem + off_par);
+      const int nv = ra.K / 8;                                   // 16-byte vectors per row
+      for (int i = threadIdx.x; i < 2 * nv; i += NCT)
+        *reinterpret_cast<uint4*>(smem + off_par + i * 16) = ldg_cached((i < nv ? ra.ln_w : ra.ln_b) + (i % nv) * 8);
+    }
+    if (ra.bias != nullptr) {
+      float* bs = reinterpret_cast<float*>(smem + off_par + 2 * 2 * KS_MAX * 2);
+      const Plan p = make_plan(ra.N, ra.K, cta, ncta);
+      if (p.tpc <= RING_BIAS_TILES) {
+        for (int i = threadIdx.x; i < p.ntile * 16; i += NCT) {
+          const int col = (p.tile0 + i / 16) * p.R + (i % 16);
+          bs[i] = (i % 16) < p.R && col < ra.N ? __bfloat162float(ra.bias[col]) : 0.f;
+        }
+        cx.bias_s = bs;
+      }
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   gemv_phase<HAS_LN, EPI, LN_BIGK>(cx, ring, ra.X, ra.bias, ra.res, ra.Y, ra.N, ra.K, ra.act, ra.ln_w, ra.ln_b, &ra.L);
 }
 

@@ -89,7 +89,12 @@ struct sv_engine {
   size_t flow_bytes = 0;
   uint32_t *f_xa = nullptr, *f_xb = nullptr, *f_qkv = nullptr, *f_att = nullptr, *f_hb = nullptr;
   unsigned long long *f_part = nullptr, *f_amax = nullptr;
-  int flow_l2_ahead = 8;            // SV_FLOW_L2AHEAD: weight slabs per CTA the producer prefetches into L2 ahead of the ring
+  int flow_l2_ahead = 0;            // SV_FLOW_L2AHEAD: weight slabs per CTA prefetched into L2 ahead of the ring (measured: no gain, off)
+  // slab-tiled copies of the decoder matrices for the dataflow kernel (made from the reference-layout weights when they change)
+  std::vector<uint8_t*> t_attn, t_proj, t_fc, t_fc2;
+  uint8_t* t_lm_head = nullptr;
+  const bf16* t_lm_src = nullptr;   // which lm_head tensor t_lm_head was made from
+  bool tiles_dirty = true;
   int flow_epoch = 0;               // phase-tag epoch: steps run through the flow kernel since the buffers were cleared
   bf16 *kscratch = nullptr, *vscratch = nullptr;   // one layer of cache, for beam-search reorders
   bf16 *kcache, *vtcache;           // [layer][max_batch][n_kv][tcap][D] / [layer][max_batch][n_kv][D][tcap]
@@ -326,7 +331,8 @@ bool build_buffers(sv_engine* e) {
   AL(mega_layers, d.n_layer); AL(mega_barrier, 4); AL(mega_dbg, 8192);
   {
     // flagged exchange buffers of the dataflow decode kernel, cleared together when a sequence starts
-    const size_t n_x = (size_t)B * H * 4, n_qkv = (size_t)B * e->qkv_cols * 4, n_hb = (size_t)B * I * 4;
+    // a flagged word per value, one 8-value fragment per 256-byte chunk (sv_decode_flow.cu FRAG_STRIDE): 32 bytes per value
+    const size_t n_x = (size_t)B * H * 32, n_qkv = (size_t)B * e->qkv_cols * 32, n_hb = (size_t)B * I * 32;
     const size_t n_part = (size_t)B * d.n_kv_head * decode_flow_max_splits() * decode_flow_partial_floats() * 8;
     const size_t n_amax = (size_t)gemv_ring_ntiles(d.vocab) * 8 * 8;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -553,12 +559,29 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
   return SV_OK;
 }
 
+// (re)build the slab-tiled copies the dataflow kernel streams, after any weight changed
+void ensure_flow_tiles(sv_engine* e, cudaStream_t st) {
+  if (!e->use_flow || (!e->tiles_dirty && e->t_lm_src == e->lm_head)) return;
+  const sv_model_desc& d = e->d;
+  const int nc = decode_flow_ncta();
+  for (int i = 0; i < d.n_layer; ++i) {
+    const DecLayer& L = e->dec[i];
+    launch_flow_repack(L.attn_w, L.attn_b, e->t_attn[i], e->qkv_cols, d.hidden, nc, st);
+    launch_flow_repack(L.proj_w, L.proj_b, e->t_proj[i], d.hidden, d.hidden, nc, st);
+    launch_flow_repack(L.fc_w, L.fc_b, e->t_fc[i], d.n_inner, d.hidden, nc, st);
+    launch_flow_repack(L.fc2_w, L.fc2_b, e->t_fc2[i], d.hidden, d.n_inner, nc, st);
+  }
+  launch_flow_repack(e->lm_head, nullptr, e->t_lm_head, d.vocab, d.hidden, nc, st);
+  e->t_lm_src = e->lm_head;
+  e->tiles_dirty = false;
+}
+
 FlowLaunch flow_launch_desc(sv_engine* e, int B) {
   FlowLaunch m{};
   m.layers_dev = e->mega_layers; m.n_layer = e->d.n_layer; m.B = B; m.H = e->d.hidden; m.I = e->d.n_inner;
   m.n_head = e->d.n_head; m.n_kv = e->d.n_kv_head; m.qkv_cols = e->qkv_cols; m.vocab = e->d.vocab; m.tcap = e->tcap;
   m.n_positions = e->d.n_positions; m.ln_eps = e->d.ln_eps; m.wte = e->wte; m.wpe = e->wpe; m.lnf_w = e->lnf_w;
-  m.lnf_b = e->lnf_b; m.lm_head = e->lm_head; m.x_plain = e->d_x; m.logits = e->logits;
+  m.lnf_b = e->lnf_b; m.lm_head = e->lm_head; m.lm_head_t = reinterpret_cast<const bf16*>(e->t_lm_head); m.x_plain = e->d_x; m.logits = e->logits;
   m.xa = e->f_xa; m.xb = e->f_xb; m.qkv = e->f_qkv; m.att = e->f_att; m.hb = e->f_hb; m.part = e->f_part; m.amax = e->f_amax;
   m.state = e->state; m.params = e->params; m.seen = e->seen; m.next_ids = e->next_ids; m.out_ids = e->out_ids;
   m.dbg = e->mega_debug ? e->mega_dbg : nullptr;
@@ -599,6 +622,7 @@ static int finish_prefill_impl(sv_engine* e, int batch, int prefix_len, float* l
   if (e->use_flow) {                 // new sequence: no word of the exchange buffers may carry a tag of the coming epochs
     SV_CK(e, cudaMemsetAsync(e->flow_mem, 0, e->flow_bytes, st));
     e->flow_epoch = 0;
+    ensure_flow_tiles(e, st);        // (no-op unless a weight changed since the last sequence)
   }
   if (last_logits) launch_logits_to_float(e->logits, last_logits, (int64_t)batch * e->d.vocab, st);
   SV_CK(e, cudaGetLastError());
@@ -675,9 +699,10 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   e->use_mega = mg && (!strcmp(mg, "1") || !strcmp(mg, "2"));   // (opt-in until it beats the graph path: DESIGN.md "decode modes")
   e->mega_realloc = mg && !strcmp(mg, "2");       // "2" = the same kernel with setmaxnreg register reallocation
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
-  { const char* fl = getenv("SV_FLOW");          // dataflow persistent kernel: default for greedy decode; "0" = per-phase graph
-    e->use_flow = !(fl && !strcmp(fl, "0")) && !e->use_mega;
-    e->flow_realloc = fl && !strcmp(fl, "2");    // "2" = three warpgroups + setmaxnreg
+  { const char* fl = getenv("SV_FLOW");          // "1": dataflow persistent kernel for greedy decode / teacher forcing (opt-in: the
+    // per-phase CUDA graph is still faster); "3": the same without setmaxnreg register reallocation
+    e->use_flow = fl && (!strcmp(fl, "1") || !strcmp(fl, "2") || !strcmp(fl, "3")) && !e->use_mega;
+    e->flow_realloc = !(fl && !strcmp(fl, "3"));
     const char* la = getenv("SV_FLOW_L2AHEAD");
     if (la) e->flow_l2_ahead = std::max(0, std::min(64, atoi(la))); }
   { const char* sg = getenv("SV_STEP_GRAPH"); e->step_graph = sg && !strcmp(sg, "1"); }
@@ -712,7 +737,27 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
     for (int i = 0; i < d.n_layer; ++i) {
       const DecLayer& L = e->dec[i];
       ml[i] = MegaLayer{L.ln1_w, L.ln1_b, L.attn_w, L.attn_b, L.proj_w, L.proj_b, L.ln2_w, L.ln2_b, L.fc_w, L.fc_b,
-                        L.fc2_w, L.fc2_b, e->kcache + e->cache_layer_stride * i, e->vtcache + e->cache_layer_stride * i};
+                        L.fc2_w, L.fc2_b, e->kcache + e->cache_layer_stride * i, e->vtcache + e->cache_layer_stride * i,
+                        nullptr, nullptr, nullptr, nullptr};
+    }
+    if (decode_flow_init() == cudaSuccess && decode_flow_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch, e->window, e->v2) &&
+        e->use_flow && e->fused_decode && d.n_layer <= 24) {
+      const int nc = decode_flow_ncta();
+      bool ok = true;
+      auto tiled = [&](int N, int K) -> uint8_t* {
+        uint8_t* p = nullptr;
+        ok = ok && dev_alloc(e, &p, (int64_t)flow_tiled_bytes(N, K, nc)) == cudaSuccess;
+        return p;
+      };
+      e->t_attn.resize(d.n_layer); e->t_proj.resize(d.n_layer); e->t_fc.resize(d.n_layer); e->t_fc2.resize(d.n_layer);
+      for (int i = 0; i < d.n_layer; ++i) {
+        e->t_attn[i] = tiled(e->qkv_cols, d.hidden); e->t_proj[i] = tiled(d.hidden, d.hidden);
+        e->t_fc[i] = tiled(d.n_inner, d.hidden); e->t_fc2[i] = tiled(d.hidden, d.n_inner);
+        ml[i].attn_t = reinterpret_cast<const bf16*>(e->t_attn[i]); ml[i].proj_t = reinterpret_cast<const bf16*>(e->t_proj[i]);
+        ml[i].fc_t = reinterpret_cast<const bf16*>(e->t_fc[i]); ml[i].fc2_t = reinterpret_cast<const bf16*>(e->t_fc2[i]);
+      }
+      e->t_lm_head = tiled(d.vocab, d.hidden);
+      if (!ok) { sv_engine_destroy(e); return fail(nullptr, SV_ERR_CUDA, "allocation of the tiled decode weights failed"); }
     }
     if (cudaMemcpy(e->mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
         decode_mega_init() != cudaSuccess || decode_flow_init() != cudaSuccess || gemv_ring_init() != cudaSuccess) {
@@ -721,7 +766,7 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
     }
     if (!decode_mega_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch) || !e->fused_decode) e->use_mega = false;
     if (e->mega_realloc && !decode_mega_realloc_supported()) e->mega_realloc = false;
-    if (!decode_flow_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch, e->window, e->v2) || !e->fused_decode) e->use_flow = false;
+    if (!decode_flow_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch, e->window, e->v2) || !e->fused_decode || d.n_layer > 24) e->use_flow = false;
     if (e->flow_realloc && !decode_flow_realloc_supported()) e->flow_realloc = false;
   }
   if (attention_decode_fused_init() != cudaSuccess || attention_decode_cluster_init() != cudaSuccess) {
@@ -802,6 +847,7 @@ int sv_engine_load_weight(sv_engine* e, const char* hf_name, const void* data, c
     SV_CK(e, cudaDeviceSynchronize());
   }
   wt.loaded = true;
+  e->tiles_dirty = true;
   return SV_OK;
 }
 
@@ -910,6 +956,7 @@ int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream
     // one token through the dataflow kernel: embed (plain) -> all layers -> logits, no selection
     const sv_model_desc& d = e->d;
     launch_embed_tokens(ids, e->wte, e->wpe, e->state, e->d_x, e->cur_batch, d.hidden, d.vocab, d.n_positions, st);
+    ensure_flow_tiles(e, st);
     FlowLaunch m = flow_launch_desc(e, e->cur_batch);
     m.nsteps = 1; m.step0 = e->flow_epoch; m.cur_len0 = e->host_cur_len; m.first_plain = 1; m.do_select = 0;
     cudaError_t ce = launch_decode_flow(m, st);
@@ -1040,6 +1087,7 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
   if (flow) {
     // dataflow persistent kernel: up to `chunk` whole tokens per cooperative launch, no host work in between
     const int chunk = (can_stop || cb) ? poll : 512;
+    ensure_flow_tiles(e, st);
     FlowLaunch m = flow_launch_desc(e, B);
     m.do_select = 1;
     if (e->mega_debug) cudaMemsetAsync(e->mega_dbg, 0, 8192 * sizeof(long long), st);

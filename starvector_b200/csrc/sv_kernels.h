@@ -121,6 +121,7 @@ void launch_select_fused(const bf16* logits, int vocab, int batch, const float* 
 struct MegaLayer {
   const bf16 *ln1_w, *ln1_b, *attn_w, *attn_b, *proj_w, *proj_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *fc2_w, *fc2_b;
   bf16 *kc, *vc;
+  const bf16 *attn_t, *proj_t, *fc_t, *fc2_t;   // slab-tiled copies for the dataflow decode kernel (sv_decode_flow.cu flow_repack_kernel)
 };
 struct MegaLaunch {
   const MegaLayer* layers_dev;
@@ -171,7 +172,7 @@ struct FlowLaunch {
   const MegaLayer* layers_dev;
   int n_layer, B, H, I, n_head, n_kv, qkv_cols, vocab, tcap, n_positions;
   float ln_eps;
-  const bf16 *wte, *wpe, *lnf_w, *lnf_b, *lm_head;
+  const bf16 *wte, *wpe, *lnf_w, *lnf_b, *lm_head, *lm_head_t;
   bf16 *x_plain, *logits;
   uint32_t *xa, *xb, *qkv, *att, *hb;          // flagged bf16 words
   unsigned long long *part, *amax;             // flagged fp32 words / argmax partials
@@ -196,5 +197,7 @@ const char* decode_flow_status();
 bool decode_flow_supported(int H, int I, int head_dim, int max_batch, int window, bool rope);
 bool decode_flow_realloc_supported();
 cudaError_t launch_decode_flow(const FlowLaunch& m, cudaStream_t st);
+size_t flow_tiled_bytes(int N, int K, int ncta);      // bytes of the slab-tiled copy of a [N][K] decode weight matrix
+void launch_flow_repack(const bf16* W, const bf16* bias, void* T, int N, int K, int ncta, cudaStream_t st);
 
 }  // namespace sv

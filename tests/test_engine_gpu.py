@@ -219,12 +219,19 @@ def test_per_row_stop_mode(tiny):
     ref = torch.full((2, width), pad, dtype=torch.long)
     for b, r in enumerate(rows):
         ref[b, :len(r)] = r
-    assert len(rows[1]) == 5                                       # row 1 stopped where the sequence first completes
+    def first_stop(seq):                                           # index after the first completion of `stop` in seq
+        for e in range(len(stop), len(seq) + 1):
+            if seq[e - len(stop):e] == stop:
+                return e
+        return len(seq)
+
+    n1 = first_stop(free[1].tolist())
+    assert len(rows[1]) == n1 <= 5                                 # row 1 stopped where the sequence first completes
     eng.encode_images(img)
     eng.prefill(torch.tensor([PROMPT] * 2))
     got = eng.generate(GenerationParams(max_new_tokens=n_new, eos_token_id=0, pad_token_id=pad, stop_ids=stop, stop_row0_only=False,
                                         poll_interval=1)).cpu().long()
-    if torch.equal(free, oracle_greedy(o16, img, PROMPT, (), n_new)[0]) and got.shape == ref.shape:
+    if got.shape == ref.shape:
         assert torch.equal(got, ref), (got.tolist(), ref.tolist())
-    else:                                                          # a tolerated bf16 flip changed a row: the stopped row must still be exact
-        assert got[1, :5].tolist() == rows[1].tolist() and (got[1, 5:] == pad).all()
+    else:                                                          # a tolerated bf16 flip changed row 0's length: the stopped row must still be exact
+        assert got[1, :n1].tolist() == rows[1].tolist() and (got[1, n1:] == pad).all()
