@@ -159,7 +159,7 @@ class OracleStarVector:
         if not kw["do_sample"]:
             kw.pop("top_p"); kw.pop("temperature")
         if kw["num_beams"] == 1:
-            kw.pop("early_stopping"); kw.pop("length_penalty")
+            kw.pop("early_stopping", None); kw.pop("length_penalty")
         if return_logits:
             kw.update(output_logits=True, return_dict_in_generate=True)
         with warnings.catch_warnings():

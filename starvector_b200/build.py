@@ -2,7 +2,7 @@
 
     python -m starvector_b200.build            # incremental
     python -m starvector_b200.build --force
-    python -m starvector_b200.build --variant nwc4     # experimental second library, see VARIANTS
+    python -m starvector_b200.build --variant timeline # second library with the dataflow kernel's timeline records, see VARIANTS
 
 The library has a plain C ABI (include/starvector_b200.h) and links only the static CUDA
 runtime, so it travels to the GPU box with the repo snapshot and loads through ctypes.
@@ -41,9 +41,8 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-# Experimental builds of the same sources (run-time selection: SV_LIB_PATH=<that .so>); never loaded by default.
+# Instrumented builds of the same sources (run-time selection: SV_LIB_PATH=<that .so>); never loaded by default.
 VARIANTS = {
-    # 4 consumer warps + producer per GEMV CTA, 3 ring slots, two CTAs per SM
     "timeline": ["-DSV_FLOW_TIMELINE=1"],     # dataflow decode kernel with its device timeline records compiled in (scripts/flow_timeline.py)
 }
 

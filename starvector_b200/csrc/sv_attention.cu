@@ -297,160 +297,7 @@ void launch_attention_decode(const bf16* qkv, int q_cols_total, const bf16* kcac
   count_launch(2);
 }
 
-// ------------------------------------------------------------------------------------------
-// Decode attention, fused: split-KV partials + CTA-level merge + "last CTA" final merge in ONE
-// kernel (PDL-ready).  grid = (ncta, n_kv, B), 8 warps per CTA; the CTA's key-block range is dealt
-// round-robin to its warps; warp partials meet in shared memory, CTA partials in an fp32 scratch;
-// the CTA that takes the last ticket of its (image, kv head) merges them in a fixed order.
-//   partial layout: [b][kvh][cta][ 16 (m) | 16 (l) | 16*D (acc) ]
 constexpr int kDecWarps = 8;
-template <int D>
-__global__ void __launch_bounds__(kDecWarps * 32) attention_decode_fused_kernel(
-    const bf16* __restrict__ qkv, int ld, const bf16* __restrict__ kcache, const bf16* __restrict__ vtcache,
-    float* __restrict__ partial, int* __restrict__ counters, bf16* __restrict__ out,
-    const GenState* __restrict__ state, int n_head, int n_kv, int tcap, float scale_log2) {
-  extern __shared__ float dsm[];                               // [kDecWarps][32 + 16*D]
-  __shared__ int s_last;
-  constexpr int PSZ = 32 + 16 * D;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int cta = blockIdx.x, ncta = gridDim.x, kvh = blockIdx.y, b = blockIdx.z;
-  const int group = n_head / n_kv;
-  const int nkeys = state->cur_len + 1;                        // this token's K/V is already in the cache
-  const int blocks = (nkeys + 31) / 32;
-  const int per = (blocks + ncta - 1) / ncta;
-  const int nact = (blocks + per - 1) / per;
-  if (cta >= nact) return;
-  const int blk0 = cta * per, blk1 = min(blocks, blk0 + per);
-  const int64_t bk = (int64_t)b * n_kv + kvh;
-
-  float acc[D / 8][4], mrow[2], lrow[2];
-  attn_init<D>(acc, mrow, lrow);
-  if (blk0 + warp < blk1) {
-    const bf16* qrow = qkv + (int64_t)b * ld + (int64_t)kvh * group * D;
-    uint32_t qa[D / 16][4];
-    load_q_frag<D, true>(qa, qrow + (int64_t)g * D, g < group, qrow + (int64_t)(g + 8) * D, g + 8 < group, t);
-    for (int blk = blk0 + warp; blk < blk1; blk += kDecWarps)
-      attn_core<D, true>(qa, kcache + bk * tcap * D, D, vtcache + bk * D * tcap, tcap, blk * 32,
-                         min(nkeys, blk * 32 + 32), scale_log2, acc, mrow, lrow, lane);
-  }
-  float* ws = dsm + warp * PSZ;
-  const float l0 = quad_sum(lrow[0]), l1 = quad_sum(lrow[1]);
-  if (t == 0) { ws[g] = mrow[0]; ws[g + 8] = mrow[1]; ws[16 + g] = l0; ws[16 + g + 8] = l1; }
-#pragma unroll
-  for (int nd = 0; nd < D / 8; ++nd) {
-    *reinterpret_cast<float2*>(ws + 32 + g * D + 8 * nd + 2 * t) = make_float2(acc[nd][0], acc[nd][1]);
-    *reinterpret_cast<float2*>(ws + 32 + (g + 8) * D + 8 * nd + 2 * t) = make_float2(acc[nd][2], acc[nd][3]);
-  }
-  __syncthreads();
-  float* pg = partial + (bk * ncta + cta) * PSZ;
-  bf16* orow = out + (int64_t)b * n_head * D + (int64_t)kvh * group * D;
-  for (int idx = threadIdx.x; idx < 16 * D; idx += kDecWarps * 32) {
-    const int r = idx / D;
-    float M = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < kDecWarps; ++w) M = fmaxf(M, dsm[w * PSZ + r]);
-    float L = 0.f, A = 0.f;
-#pragma unroll
-    for (int w = 0; w < kDecWarps; ++w) {
-      const float m = dsm[w * PSZ + r];
-      const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
-      L += dsm[w * PSZ + 16 + r] * sc;
-      A += dsm[w * PSZ + 32 + idx] * sc;
-    }
-    if (nact == 1) {                                           // short context: this CTA saw every key
-      if (r < group) orow[idx] = __float2bfloat16_rn(A / L);
-    } else {
-      pg[32 + idx] = A;
-      if (idx % D == 0) { pg[r] = M; pg[16 + r] = L; }
-    }
-  }
-  if (nact == 1) return;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[bk], 1) == nact - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // Last CTA of this (image, kv head): warp w pulls CTA partials w, w+8, ... with ONE round of independent
-  // 8-byte loads each (fragment layout), merges them in registers, and the shared-memory merge above runs again.
-  {
-    const float* p0 = partial + bk * ncta * PSZ;
-    attn_init<D>(acc, mrow, lrow);
-    float lq[2] = {0.f, 0.f};
-    for (int c = warp; c < nact; c += kDecWarps) {
-      const float* pc = p0 + (int64_t)c * PSZ;
-      const float m0 = __ldcg(pc + g), m1 = __ldcg(pc + g + 8);
-      const float pl0 = __ldcg(pc + 16 + g), pl1 = __ldcg(pc + 16 + g + 8);
-      float2 lo[D / 8], hi[D / 8];
-#pragma unroll
-      for (int nd = 0; nd < D / 8; ++nd) {
-        lo[nd] = __ldcg(reinterpret_cast<const float2*>(pc + 32 + g * D + 8 * nd + 2 * t));
-        hi[nd] = __ldcg(reinterpret_cast<const float2*>(pc + 32 + (g + 8) * D + 8 * nd + 2 * t));
-      }
-      const float n0 = fmaxf(mrow[0], m0), n1 = fmaxf(mrow[1], m1);
-      const float a0 = (mrow[0] == -INFINITY) ? 0.f : exp2f(mrow[0] - n0), b0 = (m0 == -INFINITY) ? 0.f : exp2f(m0 - n0);
-      const float a1 = (mrow[1] == -INFINITY) ? 0.f : exp2f(mrow[1] - n1), b1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - n1);
-      lq[0] = lq[0] * a0 + pl0 * b0; lq[1] = lq[1] * a1 + pl1 * b1;
-      mrow[0] = n0; mrow[1] = n1;
-#pragma unroll
-      for (int nd = 0; nd < D / 8; ++nd) {
-        acc[nd][0] = acc[nd][0] * a0 + lo[nd].x * b0; acc[nd][1] = acc[nd][1] * a0 + lo[nd].y * b0;
-        acc[nd][2] = acc[nd][2] * a1 + hi[nd].x * b1; acc[nd][3] = acc[nd][3] * a1 + hi[nd].y * b1;
-      }
-    }
-    if (t == 0) { ws[g] = mrow[0]; ws[g + 8] = mrow[1]; ws[16 + g] = lq[0]; ws[16 + g + 8] = lq[1]; }
-#pragma unroll
-    for (int nd = 0; nd < D / 8; ++nd) {
-      *reinterpret_cast<float2*>(ws + 32 + g * D + 8 * nd + 2 * t) = make_float2(acc[nd][0], acc[nd][1]);
-      *reinterpret_cast<float2*>(ws + 32 + (g + 8) * D + 8 * nd + 2 * t) = make_float2(acc[nd][2], acc[nd][3]);
-    }
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < group * D; idx += kDecWarps * 32) {
-    const int r = idx / D;
-    float M = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < kDecWarps; ++w) M = fmaxf(M, dsm[w * PSZ + r]);
-    float L = 0.f, A = 0.f;
-#pragma unroll
-    for (int w = 0; w < kDecWarps; ++w) {
-      const float m = dsm[w * PSZ + r];
-      const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
-      L += dsm[w * PSZ + 16 + r] * sc;
-      A += dsm[w * PSZ + 32 + idx] * sc;
-    }
-    orow[idx] = __float2bfloat16_rn(A / L);
-  }
-  if (threadIdx.x == 0) counters[bk] = 0;                      // re-arm for the next launch
-}
-
-int attention_decode_fused_ncta(int total_len) {
-  const int blocks = (total_len + 31) / 32;
-  return std::max(1, std::min(32, (blocks + kDecWarps - 1) / kDecWarps));
-}
-
-cudaError_t attention_decode_fused_init() {
-  return cudaFuncSetAttribute(attention_decode_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              kDecWarps * (32 + 16 * 128) * (int)sizeof(float));
-}
-
-void launch_attention_decode_fused(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache,
-                                   bf16* out, float* partial, int* counters, const GenState* state, int batch,
-                                   int n_head, int n_kv, int d, int tcap, int ncta, bool pdl, cudaStream_t st) {
-  const float scale_log2 = 1.4426950408889634f / sqrtf((float)d);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(ncta, n_kv, batch); cfg.blockDim = dim3(kDecWarps * 32);
-  cfg.dynamicSmemBytes = kDecWarps * (32 + 16 * 128) * sizeof(float); cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, attention_decode_fused_kernel<128>, qkv, q_cols_total, kcache, vtcache, partial, counters,
-                     out, state, n_head, n_kv, tcap, scale_log2);
-  count_launch();
-}
 
 // ------------------------------------------------------------------------------------------
 // Decode attention on a THREAD-BLOCK CLUSTER: the CTAs that split one image's key axis form a cluster

@@ -75,12 +75,9 @@ struct sv_engine {
   bf16 *p_x, *p_ln, *p_qkv, *p_attn, *p_h;
   bf16 *d_x, *d_ln, *d_qkv, *d_attn, *d_h, *d_last, *logits;
   float *logits_f32, *attn_partial, *amax_val;
-  int *amax_idx, *attn_counters;
-  bool mega_realloc = false;
-  bool step_graph = false;          // SV_STEP_GRAPH=1: sv_decode_step replays a captured graph (opt-in)
-  bool fused_decode = true, use_pdl = true, use_mega = false, use_ring = true, use_cluster_attn = true, use_l2_prefetch = false;
+  int* amax_idx;
+  bool fused_decode = true, use_pdl = true;
   MegaLayer* mega_layers = nullptr;
-  unsigned int* mega_barrier = nullptr;
   long long* mega_dbg = nullptr;
   bool mega_debug = false;
   // dataflow persistent decode kernel (sv_decode_flow.cu): flagged exchange buffers in one allocation
@@ -325,10 +322,9 @@ bool build_buffers(sv_engine* e) {
   AL(d_x, B * H); AL(d_ln, B * H); AL(d_qkv, B * e->qkv_cols); AL(d_attn, B * H); AL(d_h, B * I); AL(d_last, B * H);
   AL(logits, B * d.vocab); AL(logits_f32, B * d.vocab);
   AL(attn_partial, B * d.n_kv_head * kMaxSplit * (32 + 16 * D));
-  const int64_t amax_rows = std::max(gemv_ntiles(d.vocab), gemv_ring_ntiles(d.vocab));   // either lm_head kernel's tile count
+  const int64_t amax_rows = gemv_ring_ntiles(d.vocab);
   AL(amax_val, amax_rows * 8); AL(amax_idx, amax_rows * 8);
-  AL(attn_counters, B * d.n_kv_head);
-  AL(mega_layers, d.n_layer); AL(mega_barrier, 4); AL(mega_dbg, 8192);
+  AL(mega_layers, d.n_layer); AL(mega_dbg, 8192);
   {
     // flagged exchange buffers of the dataflow decode kernel, cleared together when a sequence starts
     // a flagged word per value, one 8-value fragment per 256-byte chunk (sv_decode_flow.cu FRAG_STRIDE): 32 bytes per value
@@ -361,7 +357,6 @@ bool build_buffers(sv_engine* e) {
   cudaMemset(e->vtcache, 0, (size_t)e->cache_layer_stride * d.n_layer * sizeof(bf16));
   cudaMemset(e->state, 0, sizeof(GenState));
   cudaMemset(e->flow_mem, 0, e->flow_bytes);
-  cudaMemset(e->attn_counters, 0, (size_t)B * d.n_kv_head * sizeof(int));
   return cudaMallocHost(reinterpret_cast<void**>(&e->host_flag), 64) == cudaSuccess;
 }
 
@@ -473,89 +468,41 @@ int run_decode_layers(sv_engine* e, const int32_t* ids, int B, int nsplit, cudaS
   return SV_OK;
 }
 
-// Fused decode step (sv_decode_fused.cu): 5 kernels per layer + lm_head.  `ids` != nullptr embeds those
-// tokens first (teacher forcing / sampling); with nullptr, d_x was already written by select_fused.
+// Fused decode step: 5 kernels per layer (4 weight-ring GEMVs with fused LayerNorm / bias / GELU / residual / KV append,
+// 1 cluster attention) + lm_head, chained with programmatic dependent launch.  `ids` != nullptr embeds those tokens first
+// (teacher forcing / sampling); with nullptr, d_x was already written by select_fused.
 // Leaves bf16 logits in e->logits and per-tile argmax partials in e->amax_*.
 int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, bool pdl, cudaStream_t st) {
   const sv_model_desc& d = e->d;
   const int H = d.hidden, D = d.head_dim;
   if (ids) launch_embed_tokens(ids, e->wte, e->wpe, e->state, e->d_x, B, H, d.vocab, d.n_positions, st);
   bool first = true;
-  auto attention = [&](bf16* kc, bf16* vc) {
-    if (e->use_cluster_attn || e->v2)
-      launch_attention_decode_cluster(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->state, B, d.n_head, d.n_kv_head, D,
-                                      e->tcap, std::min(ncta, 8), e->window, pdl, st);
-    else
-      launch_attention_decode_fused(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->attn_partial, e->attn_counters,
-                                    e->state, B, d.n_head, d.n_kv_head, D, e->tcap, ncta, pdl, st);
+  RingGemvLaunch g{};
+  g.B = B; g.ln_eps = d.ln_eps; g.n_head = d.n_head; g.n_kv = d.n_kv_head; g.tcap = e->tcap; g.state = e->state;
+  g.amax_val = e->amax_val; g.amax_idx = e->amax_idx;
+  auto gemv = [&](const bf16* X, const bf16* W, const bf16* bias, const bf16* res, bf16* Y, int N, int K, int act,
+                  const bf16* lw, const bf16* lb, int epi, bf16* kc, bf16* vc, bool p) {
+    g.X = X; g.W = W; g.bias = bias; g.res = res; g.Y = Y; g.N = N; g.K = K; g.act = act; g.ln_w = lw; g.ln_b = lb;
+    g.epi = epi; g.kcache = kc; g.vtcache = vc; g.pdl = p;
+    launch_gemv_ring(g, st);
   };
-  if (e->use_ring) {
-    RingGemvLaunch g{};
-    g.B = B; g.ln_eps = d.ln_eps; g.n_head = d.n_head; g.n_kv = d.n_kv_head; g.tcap = e->tcap; g.state = e->state;
-    g.amax_val = e->amax_val; g.amax_idx = e->amax_idx;
-    const bool l2pf = e->use_l2_prefetch;
-    static unsigned long long l2cap = 0;              // never ask for more than ~40% of the 126 MB L2
-    static int l2mask = -1;                           // which kernels prefetch: bit0 qkv, 1 c_proj, 2 fc, 3 mlp.c_proj, 4 lm_head
-    if (l2mask < 0) {
-      const char* m = getenv("SV_L2_PREFETCH_MASK"); l2mask = m ? atoi(m) : 31;
-      const char* c = getenv("SV_L2_PREFETCH_MB"); l2cap = (unsigned long long)(c ? atoi(c) : 48) << 20;
-    }
-    int which = 0;
-    auto gemv = [&](const bf16* X, const bf16* W, const bf16* bias, const bf16* res, bf16* Y, int N, int K, int act,
-                    const bf16* lw, const bf16* lb, int epi, bf16* kc, bf16* vc, bool p, const bf16* nextW,
-                    unsigned long long next_elems) {
-      g.X = X; g.W = W; g.bias = bias; g.res = res; g.Y = Y; g.N = N; g.K = K; g.act = act; g.ln_w = lw; g.ln_b = lb;
-      g.epi = epi; g.kcache = kc; g.vtcache = vc; g.pdl = p;
-      g.next_w = (l2pf && ((l2mask >> which) & 1)) ? nextW : nullptr;
-      g.next_bytes = std::min(next_elems * 2ull, l2cap);
-      launch_gemv_ring(g, st);
-    };
-    const unsigned long long n_qkv = (unsigned long long)e->qkv_cols * H, n_proj = (unsigned long long)H * H,
-                             n_fc = (unsigned long long)d.n_inner * H, n_lm = (unsigned long long)d.vocab * H;
-    for (int i = 0; i < d.n_layer; ++i) {
-      const DecLayer& L = e->dec[i];
-      bf16* kc = e->kcache + e->cache_layer_stride * i;
-      bf16* vc = e->vtcache + e->cache_layer_stride * i;
-      const bool last = i + 1 == d.n_layer;
-      const bf16* next_first = last ? e->lm_head : e->dec[i + 1].attn_w;       // what follows this layer's mlp.c_proj
-      which = 0;
-      gemv(e->d_x, L.attn_w, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, e->v2 ? 0 : 1, kc,
-           vc, pdl && !first, L.proj_w, n_proj);
-      first = false;
-      if (e->v2)   // RoPE on q,k then append (the GEMV epilogue cannot rotate: the pair element lives in another tile)
-        launch_rope_append(e->d_qkv, B, e->qkv_cols, d.n_head, d.n_kv_head, D, e->rope_cos, e->rope_sin, kc, vc, e->state,
-                           e->tcap, d.n_positions, pdl, st);
-      attention(kc, vc);
-      which = 1;
-      gemv(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, H, H, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl,
-           L.fc_w, n_fc);
-      which = 2;
-      gemv(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b, 0, nullptr, nullptr,
-           pdl, L.fc2_w, n_fc);
-      which = 3;
-      gemv(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl,
-           next_first, last ? n_lm : n_qkv);
-    }
-    which = 4;
-    gemv(e->d_x, e->lm_head, nullptr, nullptr, e->logits, d.vocab, H, SV_ACT_NONE, e->lnf_w, e->lnf_b, 2, nullptr, nullptr,
-         pdl, e->dec[0].attn_w, n_qkv);
-    return SV_OK;
-  }
   for (int i = 0; i < d.n_layer; ++i) {
     const DecLayer& L = e->dec[i];
     bf16* kc = e->kcache + e->cache_layer_stride * i;
     bf16* vc = e->vtcache + e->cache_layer_stride * i;
-    launch_gemv8_qkv(e->d_x, L.attn_w, L.attn_b, e->d_qkv, B, e->qkv_cols, H, L.ln1_w, L.ln1_b, d.ln_eps, kc, vc,
-                     e->state, d.n_head * D, d.n_kv_head, D, e->tcap, pdl && !first, st);
+    gemv(e->d_x, L.attn_w, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, e->v2 ? 0 : 1, kc, vc,
+         pdl && !first);
     first = false;
-    attention(kc, vc);
-    launch_gemv8(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, B, H, H, SV_ACT_NONE, nullptr, nullptr, 0.f, pdl, st);
-    launch_gemv8(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, B, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b,
-                 d.ln_eps, pdl, st);
-    launch_gemv8(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, B, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0.f, pdl, st);
+    if (e->v2)   // RoPE on q,k then append (the GEMV epilogue cannot rotate: the pair element lives in another tile)
+      launch_rope_append(e->d_qkv, B, e->qkv_cols, d.n_head, d.n_kv_head, D, e->rope_cos, e->rope_sin, kc, vc, e->state,
+                         e->tcap, d.n_positions, pdl, st);
+    launch_attention_decode_cluster(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->state, B, d.n_head, d.n_kv_head, D, e->tcap,
+                                    std::min(ncta, 8), e->window, pdl, st);
+    gemv(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, H, H, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
+    gemv(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b, 0, nullptr, nullptr, pdl);
+    gemv(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
   }
-  launch_gemv8_lmhead(e->d_x, e->lm_head, e->logits, B, d.vocab, H, e->lnf_w, e->lnf_b, d.ln_eps, e->amax_val,
-                      e->amax_idx, pdl, st);
+  gemv(e->d_x, e->lm_head, nullptr, nullptr, e->logits, d.vocab, H, SV_ACT_NONE, e->lnf_w, e->lnf_b, 2, nullptr, nullptr, pdl);
   return SV_OK;
 }
 
@@ -695,28 +642,14 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
   if (dec && !strcmp(dec, "legacy")) e->fused_decode = false;
   const char* pdl = getenv("SV_PDL");             // "0" = plain stream order between decode kernels
   if (pdl && !strcmp(pdl, "0")) e->use_pdl = false;
-  const char* mg = getenv("SV_MEGA");             // "1" = persistent multi-token kernel instead of the per-phase CUDA graph
-  e->use_mega = mg && (!strcmp(mg, "1") || !strcmp(mg, "2"));   // (opt-in until it beats the graph path: DESIGN.md "decode modes")
-  e->mega_realloc = mg && !strcmp(mg, "2");       // "2" = the same kernel with setmaxnreg register reallocation
   e->mega_debug = getenv("SV_MEGA_DEBUG") != nullptr;
   { const char* fl = getenv("SV_FLOW");          // "1": dataflow persistent kernel for greedy decode / teacher forcing (opt-in: the
     // per-phase CUDA graph is still faster); "3": the same without setmaxnreg register reallocation
-    e->use_flow = fl && (!strcmp(fl, "1") || !strcmp(fl, "2") || !strcmp(fl, "3")) && !e->use_mega;
+    e->use_flow = fl && (!strcmp(fl, "1") || !strcmp(fl, "2") || !strcmp(fl, "3")); 
     e->flow_realloc = !(fl && !strcmp(fl, "3"));
     const char* la = getenv("SV_FLOW_L2AHEAD");
     if (la) e->flow_l2_ahead = std::max(0, std::min(64, atoi(la))); }
-  { const char* sg = getenv("SV_STEP_GRAPH"); e->step_graph = sg && !strcmp(sg, "1"); }
-  const char* at = getenv("SV_ATTN");             // "ticket" = global-scratch + atomic-ticket merge instead of the cluster/DSMEM merge
-  if (at && !strcmp(at, "ticket")) e->use_cluster_attn = false;
-  const char* pf = getenv("SV_L2_PREFETCH");      // "1" = prefetch the next GEMV's weights into L2 (measured: no gain, off)
-  e->use_l2_prefetch = pf && !strcmp(pf, "1");
-  const char* rg = getenv("SV_GEMV");             // "regs" = register-landing GEMV kernels instead of the smem weight ring
-  if (rg && !strcmp(rg, "regs")) e->use_ring = false;
-  if (!gemv_ring_supported(d.hidden, true) || !gemv_ring_supported(d.n_inner, false)) e->use_ring = false;
-  // the fused step needs one of the two GEMV generations to take these widths; v2 (RoPE, K = 4608) only runs on the ring
-  const bool regs_ok = !e->v2 && gemv8_supported(d.hidden, true) && gemv8_supported(d.n_inner, false);
-  if (!e->use_ring && !regs_ok) e->fused_decode = false;
-  if (e->v2) e->use_cluster_attn = true;          // the ticket kernel has no sliding-window support
+  if (!gemv_ring_supported(d.hidden, true) || !gemv_ring_supported(d.n_inner, false)) e->fused_decode = false;
   // v2 at full size: the per-op kernels measure faster (4.4 vs 5.8 ms/token at 8B; 768-wide slabs + per-slab LayerNorm
   // on the consumer path), so the fused ring step is opt-in for v2 (SV_DECODE=fused) until that is fixed.
   if (e->v2 && !(dec && !strcmp(dec, "fused"))) e->fused_decode = false;
@@ -760,16 +693,14 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
       if (!ok) { sv_engine_destroy(e); return fail(nullptr, SV_ERR_CUDA, "allocation of the tiled decode weights failed"); }
     }
     if (cudaMemcpy(e->mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
-        decode_mega_init() != cudaSuccess || decode_flow_init() != cudaSuccess || gemv_ring_init() != cudaSuccess) {
+        decode_flow_init() != cudaSuccess || gemv_ring_init() != cudaSuccess) {
       sv_engine_destroy(e);
       return fail(nullptr, SV_ERR_CUDA, "persistent decode kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    if (!decode_mega_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch) || !e->fused_decode) e->use_mega = false;
-    if (e->mega_realloc && !decode_mega_realloc_supported()) e->mega_realloc = false;
     if (!decode_flow_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch, e->window, e->v2) || !e->fused_decode || d.n_layer > 24) e->use_flow = false;
     if (e->flow_realloc && !decode_flow_realloc_supported()) e->flow_realloc = false;
   }
-  if (attention_decode_fused_init() != cudaSuccess || attention_decode_cluster_init() != cudaSuccess) {
+  if (attention_decode_cluster_init() != cudaSuccess) {
     sv_engine_destroy(e);
     return fail(nullptr, SV_ERR_CUDA, "cannot raise the shared-memory limit of the decode attention kernel");
   }
@@ -920,39 +851,7 @@ int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream
   LaunchScope scope(e);
   cudaStream_t st = (cudaStream_t)stream;
   int r = SV_OK;
-  if (e->step_graph && e->fused_decode) {
-    // opt-in (SV_STEP_GRAPH=1): the step as ONE replayed graph instead of ~122 eager launches — what beam search and
-    // teacher forcing pay per token.  ids go through the engine's own buffer so that the captured pointers are stable.
-    const int B = e->cur_batch, nsplit = attention_decode_fused_ncta(e->host_cur_len + 1);
-    SV_CK(e, cudaMemcpyAsync(e->next_ids, ids, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    const long long key = 50000000LL + (long long)B * 100000 + nsplit * 8 + (e->use_pdl ? 4 : 0);
-    GraphEntry& ge = e->graphs[key];
-    for (int attempt = 0; attempt < 2 && !ge.exec; ++attempt) {
-      const bool pdl = e->use_pdl && attempt == 0;
-      cudaStream_t cs = e->gen_stream;
-      int64_t counted = 0;
-      g_launch_counter = &counted;
-      cudaGraph_t graph = nullptr;
-      SV_CK(e, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      r = run_decode_layers_fused(e, e->next_ids, B, nsplit, pdl, cs);
-      launch_advance_len(e->state, cs);
-      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-      g_launch_counter = &e->launches;
-      if (r != SV_OK) { if (graph) cudaGraphDestroy(graph); return r; }
-      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ge.exec, graph, 0);
-      if (graph) cudaGraphDestroy(graph);
-      if (ce != cudaSuccess) {
-        ge.exec = nullptr;
-        cudaGetLastError();
-        if (!pdl) SV_CK(e, ce);
-        e->use_pdl = false;
-        continue;
-      }
-      ge.kernels = (int)counted;
-    }
-    SV_CK(e, cudaGraphLaunch(ge.exec, st));
-    e->launches += ge.kernels;
-  } else if (e->use_flow) {
+  if (e->use_flow) {
     // one token through the dataflow kernel: embed (plain) -> all layers -> logits, no selection
     const sv_model_desc& d = e->d;
     launch_embed_tokens(ids, e->wte, e->wpe, e->state, e->d_x, e->cur_batch, d.hidden, d.vocab, d.n_positions, st);
@@ -965,7 +864,7 @@ int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void* stream
     launch_advance_len(e->state, st);
   } else {
     r = e->fused_decode
-            ? run_decode_layers_fused(e, ids, e->cur_batch, attention_decode_fused_ncta(e->host_cur_len + 1), e->use_pdl, st)
+            ? run_decode_layers_fused(e, ids, e->cur_batch, attention_decode_cluster_ncta(e->host_cur_len + 1), e->use_pdl, st)
             : run_decode_layers(e, ids, e->cur_batch, nsplit_for(e, e->host_cur_len + 1), st);
     if (r != SV_OK) return r;
     launch_advance_len(e->state, st);
@@ -1011,7 +910,7 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
   // HF stop rules and embeds the token for the first decode step.
   const bool fused = e->fused_decode;
   const bool fused_select = fused && !p->do_sample;
-  const int ntiles = e->use_ring ? gemv_ring_ntiles(e->d.vocab) : gemv_ntiles(e->d.vocab);   // equal in the default build
+  const int ntiles = gemv_ring_ntiles(e->d.vocab);
   auto select_step = [&](int advance_len, bool have_partials, bool pdl) {
     if (fused_select) {
       launch_select_fused(e->logits, e->d.vocab, B, have_partials ? e->amax_val : nullptr, e->amax_idx, ntiles, e->state,
@@ -1024,11 +923,11 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
   };
   select_step(/*advance_len=*/0, /*have_partials=*/false, /*pdl=*/false);
 
-  const int nsplit = fused ? attention_decode_fused_ncta(e->prefix_len + max_new) : nsplit_for(e, e->prefix_len + max_new);
+  const int nsplit = fused ? attention_decode_cluster_ncta(e->prefix_len + max_new) : nsplit_for(e, e->prefix_len + max_new);
   const long long key = (long long)B * 100000 + nsplit * 8 + (p->do_sample ? 1 : 0) + (fused ? 2 : 0) + (e->use_pdl ? 4 : 0);
   GraphEntry& ge = e->graphs[key];
   const bool flow = e->use_flow && fused_select;
-  if (!ge.exec && max_new > 1 && !(e->use_mega && fused_select) && !flow) {
+  if (!ge.exec && max_new > 1 && !flow) {
     for (int attempt = 0; attempt < 2 && !ge.exec; ++attempt) {
       const bool pdl = e->use_pdl && fused && attempt == 0;
       int64_t counted = 0;
@@ -1057,7 +956,6 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
 
   const int poll = p->poll_interval > 0 ? p->poll_interval : 16;
   const bool can_stop = p->eos_token_id >= 0 || p->n_stop_ids > 0;
-  const bool mega = e->use_mega && fused_select && !flow;
   // streaming: at every poll, tokens [emitted, step) of every row go to the callback through a pinned staging buffer
   int emitted = 0;
   bool cancelled = false;
@@ -1113,38 +1011,7 @@ static int generate_impl(sv_engine* e, const sv_gen_params* p, int32_t* out_ids,
       }
     }
   }
-  if (mega) {
-    // persistent kernel: up to `chunk` whole tokens per cooperative launch, no host work in between
-    const int chunk = (can_stop || cb) ? poll : 256;
-    MegaLaunch m{};
-    m.layers_dev = e->mega_layers; m.n_layer = e->d.n_layer; m.B = B; m.H = e->d.hidden; m.I = e->d.n_inner;
-    m.n_head = e->d.n_head; m.n_kv = e->d.n_kv_head; m.qkv_cols = e->qkv_cols; m.vocab = e->d.vocab; m.tcap = e->tcap;
-    m.n_positions = e->d.n_positions; m.ln_eps = e->d.ln_eps; m.wte = e->wte; m.wpe = e->wpe; m.lnf_w = e->lnf_w;
-    m.lnf_b = e->lnf_b; m.lm_head = e->lm_head; m.x = e->d_x; m.qkv = e->d_qkv; m.attn = e->d_attn; m.h = e->d_h;
-    m.logits = e->logits; m.attn_partial = e->attn_partial; m.amax_val = e->amax_val; m.amax_idx = e->amax_idx;
-    m.state = e->state; m.params = e->params; m.seen = e->seen; m.next_ids = e->next_ids; m.out_ids = e->out_ids;
-    m.barrier_ctr = e->mega_barrier; m.att_ncta = nsplit;
-    m.dbg = e->mega_debug ? e->mega_dbg : nullptr;
-    m.realloc = e->mega_realloc;
-    if (e->mega_debug) cudaMemsetAsync(e->mega_dbg, 0, 1024 * sizeof(long long), st);
-    int left = max_new - 1;
-    while (left > 0 && !done) {
-      m.nsteps = std::min(left, chunk);
-      cudaError_t ce = launch_decode_mega(m, st);
-      if (ce != cudaSuccess) return fail(e, SV_ERR_CUDA, "persistent decode launch failed: %s", cudaGetErrorString(ce));
-      left -= m.nsteps;
-      steps += m.nsteps;
-      if (cb && left > 0) {
-        const int r = poll_device(done);
-        if (r != SV_OK) return r;
-      } else if (can_stop && left > 0) {
-        SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->state->done, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        SV_CK(e, cudaStreamSynchronize(st));
-        done = e->host_flag[0] != 0;
-      }
-    }
-  }
-  for (int s = 1; s < max_new && !done && !mega && !flow; ++s) {
+  for (int s = 1; s < max_new && !done && !flow; ++s) {
     SV_CK(e, cudaGraphLaunch(ge.exec, st));
     e->launches += ge.kernels;
     ++steps;
@@ -1251,9 +1118,9 @@ int sv_debug_read_timeline(sv_engine* e, long long* out_host, int32_t n) {
 const char* sv_engine_describe(sv_engine* e) {
   if (!e) return "";
   char buf[512];
-  snprintf(buf, sizeof(buf), "decode=%s attn=%s pdl=%d l2pf=%d linear_impl=%d mega[%s]",
-           !e->fused_decode ? "legacy-kernels" : e->use_flow ? (e->flow_realloc ? "dataflow-kernel-setmaxnreg" : "dataflow-kernel") : (e->use_mega ? (e->mega_realloc ? "persistent-kernel-setmaxnreg" : "persistent-kernel") : (e->use_ring ? "ring-gemv-graph" : "reg-gemv-graph")),
-           e->use_cluster_attn ? "cluster-dsmem" : "ticket", (int)e->use_pdl, (int)e->use_l2_prefetch, e->linear_impl, decode_mega_status());
+  snprintf(buf, sizeof(buf), "decode=%s attn=cluster-dsmem pdl=%d linear_impl=%d flow[%s]",
+           !e->fused_decode ? "legacy-kernels" : e->use_flow ? (e->flow_realloc ? "dataflow-kernel-setmaxnreg" : "dataflow-kernel") : "ring-gemv-graph",
+           (int)e->use_pdl, e->linear_impl, decode_flow_status());
   e->describe = buf;
   return e->describe.c_str();
 }

@@ -88,58 +88,24 @@ void launch_rope_append(bf16* qkv, int batch, int qkv_cols, int n_head, int n_kv
                         bool pdl, cudaStream_t st);
 void launch_rope_table(bf16* cos_t, bf16* sin_t, int max_pos, int d, float theta, cudaStream_t st);
 
-// fused decode attention (PDL-ready): ncta from attention_decode_fused_ncta(max total length)
-int attention_decode_fused_ncta(int total_len);
-cudaError_t attention_decode_fused_init();
-void launch_attention_decode_fused(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache,
-                                   bf16* out, float* partial, int* counters, const GenState* state, int batch,
-                                   int n_head, int n_kv, int d, int tcap, int ncta, bool pdl, cudaStream_t st);
-
-// cluster / distributed-shared-memory variant (default): ncta <= 8 CTAs of one image form a cluster
+// decode attention (PDL-ready): the ncta <= 8 CTAs of one image form a thread-block cluster
 int attention_decode_cluster_ncta(int total_len);
 cudaError_t attention_decode_cluster_init();
 cudaError_t launch_attention_decode_cluster(const bf16* qkv, int q_cols_total, const bf16* kcache, const bf16* vtcache,
                                             bf16* out, const GenState* state, int batch, int n_head, int n_kv, int d,
                                             int tcap, int ncta, int window, bool pdl, cudaStream_t st);
 
-// ---- sv_decode_fused.cu : decode-step GEMVs with fused LayerNorm / KV append / argmax, PDL-ready
-bool gemv8_supported(int K, bool has_ln);
-int gemv_ntiles(int N);   // number of argmax partial rows the lm_head epilogue writes
-void launch_gemv8(const bf16* x, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int B, int N, int K,
-                  int act, const bf16* ln_w, const bf16* ln_b, float ln_eps, bool pdl, cudaStream_t st);
-void launch_gemv8_qkv(const bf16* x, const bf16* w, const bf16* bias, bf16* y, int B, int N, int K, const bf16* ln_w,
-                      const bf16* ln_b, float ln_eps, bf16* kcache, bf16* vtcache, const GenState* state, int q_cols,
-                      int n_kv, int d, int tcap, bool pdl, cudaStream_t st);
-void launch_gemv8_lmhead(const bf16* x, const bf16* w, bf16* logits, int B, int N, int K, const bf16* ln_w,
-                         const bf16* ln_b, float ln_eps, float* amax_val, int* amax_idx, bool pdl, cudaStream_t st);
+// ---- sv_decode_fused.cu : token selection fused with the next step's embedding, PDL-ready
 void launch_select_fused(const bf16* logits, int vocab, int batch, const float* amax_val, const int* amax_idx,
                          int ntiles, GenState* state, const GenParamsDev* params, uint8_t* seen, int32_t* next_ids,
                          int32_t* out_ids, int advance_len, const bf16* wte, const bf16* wpe, bf16* x, int h,
                          int n_positions, bool pdl, cudaStream_t st);
 
-// ---- sv_decode_mega.cu : persistent multi-token decode kernel (cooperative launch, one CTA per SM)
+// ---- sv_decode_mega.cu : per-phase weight-ring decode GEMV; layer descriptor shared with sv_decode_flow.cu
 struct MegaLayer {
   const bf16 *ln1_w, *ln1_b, *attn_w, *attn_b, *proj_w, *proj_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *fc2_w, *fc2_b;
   bf16 *kc, *vc;
   const bf16 *attn_t, *proj_t, *fc_t, *fc2_t;   // slab-tiled copies for the dataflow decode kernel (sv_decode_flow.cu flow_repack_kernel)
-};
-struct MegaLaunch {
-  const MegaLayer* layers_dev;
-  int n_layer, B, H, I, n_head, n_kv, qkv_cols, vocab, tcap, n_positions;
-  float ln_eps;
-  const bf16 *wte, *wpe, *lnf_w, *lnf_b, *lm_head;
-  bf16 *x, *qkv, *attn, *h, *logits;
-  float* attn_partial;
-  float* amax_val;
-  int* amax_idx;
-  GenState* state;
-  const GenParamsDev* params;
-  uint8_t* seen;
-  int32_t *next_ids, *out_ids;
-  unsigned int* barrier_ctr;
-  int nsteps, att_ncta;
-  long long* dbg;
-  bool realloc;        // SV_MEGA=2: three warpgroups with setmaxnreg register reallocation
 };
 // one-phase weight-ring GEMV (same device code as the persistent kernel's GEMV phases)
 struct RingGemvLaunch {
@@ -153,20 +119,11 @@ struct RingGemvLaunch {
   float* amax_val;
   int* amax_idx;
   bool pdl;
-  const void* next_w;               // next GEMV's weight matrix to prefetch into L2 (nullptr = none)
-  unsigned long long next_bytes;
 };
 cudaError_t gemv_ring_init();
 bool gemv_ring_supported(int K, bool has_ln);
 int gemv_ring_ntiles(int N);
 void launch_gemv_ring(const RingGemvLaunch& g, cudaStream_t st);
-cudaError_t decode_mega_init();
-int decode_mega_ncta();
-const char* decode_mega_status();
-bool decode_mega_supported(int H, int I, int head_dim, int max_batch);
-bool decode_mega_realloc_supported();
-cudaError_t launch_decode_mega(const MegaLaunch& m, cudaStream_t st);
-
 // ---- sv_decode_flow.cu : dataflow persistent decode kernel (flagged activation words through L2, no grid barriers)
 struct FlowLaunch {
   const MegaLayer* layers_dev;

@@ -235,3 +235,34 @@ def test_per_row_stop_mode(tiny):
         assert torch.equal(got, ref), (got.tolist(), ref.tolist())
     else:                                                          # a tolerated bf16 flip changed row 0's length: the stopped row must still be exact
         assert got[1, :n1].tolist() == rows[1].tolist() and (got[1, n1:] == pad).all()
+
+
+@pytest.mark.parametrize("twin_below", [True, False])
+def test_greedy_tie_takes_the_lowest_index(tiny, twin_below):
+    """HF greedy = argmax over the bf16 logits cast to float, lowest index wins ties.  An un-tied lm_head
+    with two IDENTICAL rows gives two exactly equal logits at every step: the engine must emit the smaller index, on the
+    first token (prefill logits) and on every decode step (lm_head argmax partials), in both decode modes' shared epilogue."""
+    d, sd, eng, o16, o32, img = tiny
+    eng.encode_images(img[:1])
+    top = int(eng.prefill(torch.tensor([PROMPT]), return_logits=True)[0].float().argmax())
+    twin = top - 3 if (twin_below and top >= 3) else top + 5
+    assert 0 < twin < d.vocab - 8
+    head = sd["model.svg_transformer.transformer.transformer.wte.weight"].clone()
+    head[twin] = head[top]
+    sd2 = dict(sd)
+    sd2["model.svg_transformer.transformer.lm_head.weight"] = head
+    eng2 = Engine(d, 0)
+    eng2.load_state_dict(sd2)
+    eng2.encode_images(img[:1])
+    lg = eng2.prefill(torch.tensor([PROMPT]), return_logits=True)[0].float()
+    assert lg[twin] == lg[top] == lg.max()
+    got = eng2.generate(GenerationParams(max_new_tokens=6, eos_token_id=None, pad_token_id=d.vocab - 4)).cpu()
+    assert int(got[0, 0]) == min(top, twin)
+    # every later step: wherever the two twins are the maximum, the smaller index must have been chosen
+    eng2.encode_images(img[:1])
+    eng2.prefill(torch.tensor([PROMPT]))
+    for s in range(5):
+        step_logits = eng2.decode_step(got[:, s])[0].float()
+        if step_logits[top] == step_logits.max():
+            assert int(got[0, s + 1]) == min(top, twin), (s, int(got[0, s + 1]))
+    eng2.close()
