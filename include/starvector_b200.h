@@ -140,6 +140,12 @@ SV_API int sv_decode_step(sv_engine* e, const int32_t* ids, float* logits, void*
 /* Beam search support: permute the image rows of the KV cache, row r <- row src_rows[r]
  * (int32 [B] on the device) for the tokens cached so far = HF `_reorder_cache` (vendored modeling_gpt_bigcode.py:1282-1291). */
 SV_API int sv_reorder_cache(sv_engine* e, const int32_t* src_rows, void* stream);
+/* Prefix-KV sharing (reference starvector_base.py:261-286 `num_return_sequences`, starvector_arch.py:161-184
+ * `vision_embeds.repeat(num_generations, 1, 1)`): directly after sv_prefill / sv_prefill_embeds of b rows, make the engine hold
+ * new_batch rows where row r is a copy of prefilled row src_rows_host[r] (HOST int32 [new_batch]): KV cache, last-position
+ * logits and generation state are replicated, so the visual prefix is encoded and prefilled once per image, not once per
+ * completion.  new_batch <= max_batch. */
+SV_API int sv_expand_batch(sv_engine* e, const int32_t* src_rows_host, int32_t new_batch, void* stream);
 /* GenerationMixin.generate() after the prefill (greedy / sampling loop, App. B): runs up to
  * max_new_tokens steps as a replayed CUDA graph.  out_ids int32 [B,max_new_tokens] (new tokens
  * only, padded with pad_token_id), out_len int32 [B] = rectangular generated length.

@@ -63,6 +63,7 @@ SIGNATURES = {
     "sv_prefill_embeds": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "sv_decode_step": (C.c_int, [_P, _P, _P, _P]),
     "sv_reorder_cache": (C.c_int, [_P, _P, _P]),
+    "sv_expand_batch": (C.c_int, [_P, _P, C.c_int32, _P]),
     "sv_generate": (C.c_int, [_P, C.POINTER(GenParams), _P, _P, _P]),
     "sv_generate_stream": (C.c_int, [_P, C.POINTER(GenParams), _P, _P, TOKEN_CALLBACK, _P, _P]),
     "sv_generate_im2svg_host": (C.c_int, [_P, _P, _I, _P, _I, C.POINTER(GenParams), _P, _P, _P]),

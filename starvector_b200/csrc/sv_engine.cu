@@ -1107,6 +1107,34 @@ int sv_reorder_cache(sv_engine* e, const int32_t* src_rows, void* stream) {
   return SV_OK;
 }
 
+int sv_expand_batch(sv_engine* e, const int32_t* src_rows_host, int32_t new_batch, void* stream) {
+  if (!e || !src_rows_host) return fail(e, SV_ERR_INVALID, "null argument");
+  if (!e->prefilled || e->host_cur_len != e->prefix_len) return fail(e, SV_ERR_STATE, "sv_expand_batch must directly follow sv_prefill");
+  if (new_batch < 1 || new_batch > e->d.max_batch) return fail(e, SV_ERR_INVALID, "new_batch %d outside [1,%d]", new_batch, e->d.max_batch);
+  for (int r = 0; r < new_batch; ++r)
+    if (src_rows_host[r] < 0 || src_rows_host[r] >= e->cur_batch) return fail(e, SV_ERR_INVALID, "src_rows[%d] = %d is not a prefilled row", r, src_rows_host[r]);
+  SV_CK(e, cudaSetDevice(e->device));
+  LaunchScope scope(e);
+  cudaStream_t st = (cudaStream_t)stream;
+  const sv_model_desc& d = e->d;
+  const int len = e->host_cur_len;
+  SV_CK(e, cudaMemcpyAsync(e->ids_tmp, src_rows_host, (size_t)new_batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < d.n_layer; ++i) {          // cache rows: gather through the one-layer scratch (as sv_reorder_cache)
+    bf16* kc = e->kcache + e->cache_layer_stride * i;
+    bf16* vc = e->vtcache + e->cache_layer_stride * i;
+    launch_kv_gather(kc, vc, e->kscratch, e->vscratch, e->ids_tmp, new_batch, d.n_kv_head, e->tcap, d.head_dim, len, st);
+    launch_kv_gather(e->kscratch, e->vscratch, kc, vc, nullptr, new_batch, d.n_kv_head, e->tcap, d.head_dim, len, st);
+  }
+  // the prefill's last-position logits (token 0 is selected from them) and the last hidden row, staged through logits_f32
+  const size_t row = (size_t)d.vocab * sizeof(bf16);
+  uint8_t* stage = reinterpret_cast<uint8_t*>(e->logits_f32);
+  for (int r = 0; r < new_batch; ++r)
+    SV_CK(e, cudaMemcpyAsync(stage + r * row, reinterpret_cast<uint8_t*>(e->logits) + src_rows_host[r] * row, row, cudaMemcpyDeviceToDevice, st));
+  SV_CK(e, cudaMemcpyAsync(e->logits, stage, new_batch * row, cudaMemcpyDeviceToDevice, st));
+  e->cur_batch = new_batch;
+  return finish_prefill_impl(e, new_batch, e->prefix_len, nullptr, st);     // fresh GenState for the new rows, exchange buffers cleared
+}
+
 int64_t sv_launch_count(const sv_engine* e) { return e ? e->launches : 0; }
 
 int sv_debug_read_timeline(sv_engine* e, long long* out_host, int32_t n) {

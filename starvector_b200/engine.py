@@ -206,6 +206,14 @@ class Engine:
         with self._lock:
             self._ck(self._lib.sv_reorder_cache(self._h, C.c_void_p(idx.data_ptr()), _stream_ptr(self.device)))
 
+    def expand_batch(self, src_rows) -> None:
+        """Prefix-KV sharing: right after a prefill, row r of the new batch becomes a copy of prefilled row src_rows[r]."""
+        rows = [int(r) for r in src_rows]
+        arr = (C.c_int32 * len(rows))(*rows)
+        with self._lock:
+            self._ck(self._lib.sv_expand_batch(self._h, arr, len(rows), _stream_ptr(self.device)))
+        self._batch = len(rows)
+
     def generate(self, params: GenerationParams, on_tokens=None) -> torch.Tensor:
         """Run the decode loop after a prefill. Returns int32 [B, n_generated] (new tokens only).
 

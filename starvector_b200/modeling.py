@@ -221,9 +221,13 @@ class StarVectorStarCoder:
                 out = self.engine.generate(params, on_tokens=on_tokens)
             finally:
                 streamer.end()
-        elif image.shape[0] <= mb:
+        elif image.shape[0] * int(kwargs.get("_share_prefix", 1)) <= mb:
             self.engine.encode_images(image)
             self.engine.prefill(prompt_ids)
+            G = int(kwargs.get("_share_prefix", 1))
+            if G > 1:      # num_return_sequences: the visual prefix is encoded and prefilled ONCE per image, its KV rows replicated
+                self.engine.expand_batch([r // G for r in range(image.shape[0] * G)])
+                prompt_ids = prompt_ids.repeat_interleave(G, dim=0)
             out = self.engine.generate(params)
         else:
             # More images than the engine holds at once: run max_batch-sized groups one after another and rebuild the
@@ -244,7 +248,8 @@ class StarVectorStarCoder:
 
     def generate_im2svg_grpo(self, batch, **kwargs):                                               # :261-286
         """`num_return_sequences` completions per image (sampled independently, `num_beams` forced to 1, :277-280):
-        HF's `_expand_inputs_for_generation` = every image row repeated G times, adjacent.  Returns the reference's dict;
+        HF's `_expand_inputs_for_generation` = every image row repeated G times, adjacent — here the image is encoded and
+        prefilled once and its KV-cache rows are replicated (`sv_expand_batch`).  Returns the reference's dict;
         `outputs` is `[B*G, P + n_new]`, `inputs_embeds` the un-expanded `[B, Q+P, H]` prefix embeddings."""
         G = int(kwargs.get("num_return_sequences", 1))
         if G < 1:
@@ -255,12 +260,19 @@ class StarVectorStarCoder:
                 raise ValueError(f"batch {image.shape[0]} x num_return_sequences {G} exceeds the engine's max_batch "
                                  f"{self.engine.dims.max_batch}")
             kwargs = dict(kwargs, num_beams=1)                 # :277-280 (only when num_return_sequences > 1)
-        ids = self.generate_im2svg_ids({"image": image.repeat_interleave(G, dim=0) if G > 1 else image}, **kwargs)
+        ids = self.generate_im2svg_ids({"image": image}, **(dict(kwargs, _share_prefix=G) if G > 1 else kwargs))
         emb, _ = self.engine.encode_images(image, return_embeds=True)
         prompt_ids = self._tokenize_prompt(kwargs.get("prompt"), image.shape[0])
         inputs_embeds = torch.cat([emb, self._get_embeddings(prompt_ids.to(emb.device))], dim=1)    # :217-219
         return {"raw_svg": self.svg_transformer.tokenizer.batch_decode(ids, skip_special_tokens=True),
                 "outputs": ids, "inputs_embeds": inputs_embeds}
+
+
+@dataclasses.dataclass
+class _ScoreOutput:
+    """The two fields of `CausalLMOutputWithCrossAttentions` the RLRF scoring callers read."""
+    loss: Optional[torch.Tensor]
+    logits: torch.Tensor
 
 
 def read_checkpoint(path: str):
@@ -346,6 +358,45 @@ class StarVectorForCausalLM:
 
     def save_pretrained(self, path: str, state_dict: Dict[str, torch.Tensor]) -> None:
         write_checkpoint(path, self.config, state_dict)
+
+    # -- scoring (starvector_arch.py:161-184) ------------------------------------------------
+    @torch.no_grad()
+    def forward(self, vision_embeds: torch.Tensor, input_ids: torch.Tensor, num_generations: int = 1,
+                attention_mask: Optional[torch.Tensor] = None, num_logits_to_keep: int = 0):
+        """Logits of `num_generations` completions per image over a shared visual prefix, as the reference's
+        `StarVectorForCausalLM.forward`: `inputs_embeds = cat([vision_embeds.repeat(G, 1, 1), wte(input_ids)], 1)` -> decoder
+        -> `lm_head` on the last `num_logits_to_keep` positions (all completion positions when 0).  Here the prefix is
+        prefilled ONCE per image and its KV rows replicated (`sv_expand_batch`, rows r % b as `.repeat` orders them); the
+        completion is teacher-forced through `sv_decode_step`.  Returns an object with `.logits` fp32 `[b*G, n_keep, V]`
+        and `.loss = None`.  `attention_mask` may only mask a right-padded tail (what GRPO completions carry)."""
+        eng = self.model.engine
+        b, G = vision_embeds.shape[0], int(num_generations)
+        ids = input_ids.to(eng.device)
+        if ids.shape[0] != b * G:
+            raise ValueError(f"input_ids has {ids.shape[0]} rows, expected vision rows {b} x num_generations {G}")
+        if b * G > eng.dims.max_batch:
+            raise ValueError(f"{b} x {G} rows exceed the engine's max_batch {eng.dims.max_batch}")
+        T = ids.shape[1]
+        if attention_mask is not None:
+            m = attention_mask.to(torch.bool)
+            tail = m[:, m.shape[1] - T:] if m.shape[1] >= T else m
+            if not bool(torch.all(m[:, : m.shape[1] - T])) or bool(torch.any(tail[:, 1:] & ~tail[:, :-1])):
+                raise NotImplementedError("only right-padded completions (mask = ones then zeros) are supported")
+        n_keep = T if int(num_logits_to_keep) <= 0 else int(num_logits_to_keep)
+        if n_keep > T:
+            raise NotImplementedError("num_logits_to_keep beyond the completion (prefix positions) is not built")
+        eng.prefill_embeds(vision_embeds.to(eng.device, torch.bfloat16))
+        if G > 1:
+            eng.expand_batch([r % b for r in range(b * G)])
+        out = torch.empty(b * G, n_keep, eng.dims.vocab, dtype=torch.float32, device=eng.device)
+        for t in range(T):
+            keep = t >= T - n_keep
+            lg = eng.decode_step(ids[:, t], return_logits=keep)
+            if keep:
+                out[:, t - (T - n_keep)] = lg
+        return _ScoreOutput(loss=None, logits=out)
+
+    __call__ = forward
 
     # -- nn.Module-ish no-ops the callers use (quickstart.py:11-12) ------------------------
     def cuda(self, *a, **k): return self

@@ -81,7 +81,7 @@ def test_grpo_num_return_sequences(model):
     two = m.model.generate_im2svg_grpo({"image": img}, use_nucleus_sampling=False, num_return_sequences=2, **kw)
     assert two["outputs"].shape[0] == 4 and len(two["raw_svg"]) == 4
     assert torch.equal(two["outputs"][0], two["outputs"][1]) and torch.equal(two["outputs"][2], two["outputs"][3])
-    one = m.model.generate_im2svg_grpo({"image": img}, use_nucleus_sampling=False, **kw)
+    one = m.model.generate_im2svg_grpo({"image": img}, use_nucleus_sampling=False, num_beams=1, **kw)   # (G = 1 keeps the default 2 beams, :277-280)
     assert torch.equal(one["outputs"], two["outputs"][::2])
     assert two["inputs_embeds"].shape == (2, d.query_length + P, d.hidden)
     s = m.model.generate_im2svg_grpo({"image": img[:1]}, num_return_sequences=4, temperature=2.0, top_p=1.0, **kw)
@@ -89,6 +89,58 @@ def test_grpo_num_return_sequences(model):
     assert len({tuple(r.tolist()) for r in s["outputs"]}) >= 3          # independent samples per copy
     with pytest.raises(ValueError):
         m.model.generate_im2svg_grpo({"image": img}, num_return_sequences=3, **kw)      # 6 rows > max_batch 4
+
+
+def test_forward_scoring_matches_oracle(model):
+    """`StarVectorForCausalLM.forward` (starvector_arch.py:161-184): logits of G completions per image over a shared visual
+    prefix (prefilled once, KV rows replicated in `.repeat` order), against the oracle's one full forward."""
+    from oracle.pipeline import OracleStarVector
+
+    d, sd, m = model
+    img = synthetic_images(d, 2, seed=1).cuda()
+    grpo = m.model.generate_im2svg_grpo({"image": img}, use_nucleus_sampling=False, num_beams=1, max_length=d.query_length + 2 + 1)
+    vision_embeds = grpo["inputs_embeds"]                                   # [2, Q+P, H], the reference's hand-over to forward()
+    G, T, keep = 2, 9, 5
+    gen = torch.Generator().manual_seed(11)
+    ids = torch.randint(1, d.vocab - 8, (2 * G, T), generator=gen)
+    mask = torch.ones(2 * G, vision_embeds.shape[1] + T, dtype=torch.long)
+    mask[1, -2:] = 0                                                         # a right-padded completion is accepted
+    out = m(vision_embeds, ids, G, mask, keep)
+    assert out.loss is None and out.logits.shape == (2 * G, keep, d.vocab)
+    full = m.forward(vision_embeds, ids, num_generations=G, attention_mask=None, num_logits_to_keep=0).logits
+    assert full.shape == (2 * G, T, d.vocab) and torch.equal(full[:, -keep:], out.logits)
+    refs = {}
+    for dt in (torch.bfloat16, torch.float32):
+        o = OracleStarVector(d, sd, dtype=dt, pad_token_id=d.vocab - 4)
+        emb = torch.cat([vision_embeds.cpu().to(dt).repeat(G, 1, 1), o.llm.transformer.wte(ids)], dim=1)
+        with torch.no_grad():
+            refs[dt] = o.llm(inputs_embeds=emb, use_cache=False).logits[:, -T:].float()
+    e = (full.cpu() - refs[torch.float32]).abs()
+    o_err = (refs[torch.bfloat16] - refs[torch.float32]).abs()
+    assert e.max().item() <= 2.0 * o_err.max().item() + 3e-2 and e.mean().item() <= 2.0 * o_err.mean().item() + 3e-3, \
+        (e.max().item(), o_err.max().item(), e.mean().item(), o_err.mean().item())
+    with pytest.raises(NotImplementedError):
+        left = mask.clone(); left[0, 0] = 0
+        m(vision_embeds, ids, G, left, keep)
+    with pytest.raises(ValueError):
+        m(vision_embeds, ids[:3], G, None, keep)
+
+
+def test_grpo_shares_the_visual_prefix(model):
+    """num_return_sequences = G runs ONE encode + prefill per image (KV rows replicated), not G: fewer launches, same tokens."""
+    d, sd, m = model
+    img = synthetic_images(d, 2, seed=1).cuda()
+    P = len(m.model.svg_transformer.tokenizer("<svg")["input_ids"])
+    kw = dict(use_nucleus_sampling=False, max_length=d.query_length + P + 6)
+    eng = m.model.engine
+    n0 = eng.launch_count()
+    shared = m.model.generate_im2svg_grpo({"image": img}, num_return_sequences=2, **kw)["outputs"]
+    n_shared = eng.launch_count() - n0
+    n0 = eng.launch_count()
+    plain = m.model.generate_im2svg_ids({"image": img.repeat_interleave(2, dim=0)}, num_beams=1, **kw)
+    n_plain = eng.launch_count() - n0
+    assert torch.equal(shared.cpu(), plain.cpu())
+    assert n_shared < n_plain, (n_shared, n_plain)
 
 
 def test_more_images_than_max_batch_runs_in_groups(model):
