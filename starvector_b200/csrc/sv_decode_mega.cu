@@ -327,6 +327,7 @@ struct RingGemvArgs {
   Args a;            // B, ln_eps, n_head, n_kv, tcap, state, amax_* (fields the epilogues read)
   Layer L;           // kc / vc for the QKV epilogue
   const bf16 *X, *W, *bias, *res, *ln_w, *ln_b;
+  const uint8_t* Wt; // slab-tiled copy of W (one bulk copy per ring slot) or nullptr
   bf16* Y;
   int N, K, act;
   int nslots;        // ring depth of THIS launch
@@ -377,7 +378,8 @@ __global__ void __launch_bounds__(NTHREADS, RING_MINBLOCKS) gemv_ring_kernel(con
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == NWC) {
-    produce_phase(ring, ra.W, ra.N, ra.K, cta, ncta, lane);     // no dependency on the previous kernel
+    if (ra.Wt != nullptr) produce_phase_tiled(ring, ra.Wt, ra.N, ra.K, cta, ncta, lane);
+    else produce_phase(ring, ra.W, ra.N, ra.K, cta, ncta, lane);     // no dependency on the previous kernel
     if constexpr (EPI == EPI_QKV)
       l2_prefetch_kv(ra.L.kc, ra.L.vc, ra.a.state->cur_len, ra.a.B * ra.a.n_kv, ra.a.tcap, cta, ncta, lane);
     return;
@@ -449,7 +451,7 @@ bool gemv_ring_supported(int K, bool has_ln) { (void)has_ln; return K >= 32 && K
 // CTAs of one ring GEMV: one per SM in every build.  With RING_MINBLOCKS = 2 the CTA is small enough for two per SM, and
 // the second slot is deliberately left free: it is where the NEXT kernel's CTA (launched early through PDL) becomes
 // resident and starts filling its ring while this kernel is still computing.
-static int ring_ncta() {
+int gemv_ring_ncta() {
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -457,7 +459,7 @@ static int ring_ncta() {
 }
 
 int gemv_ring_ntiles(int N) {
-  const int nsm = ring_ncta();
+  const int nsm = gemv_ring_ncta();
   const int rows_per_cta = (N + nsm - 1) / nsm, tpc = (rows_per_cta + 15) / 16, R = (rows_per_cta + tpc - 1) / tpc;
   return (N + R - 1) / R;
 }
@@ -467,9 +469,9 @@ void launch_gemv_ring(const RingGemvLaunch& g, cudaStream_t st) {
   ra.a.B = g.B; ra.a.ln_eps = g.ln_eps; ra.a.n_head = g.n_head; ra.a.n_kv = g.n_kv; ra.a.tcap = g.tcap; ra.a.state = const_cast<GenState*>(g.state);
   ra.a.amax_val = g.amax_val; ra.a.amax_idx = g.amax_idx;
   ra.L.kc = g.kcache; ra.L.vc = g.vtcache;
-  ra.X = g.X; ra.W = g.W; ra.bias = g.bias; ra.res = g.res; ra.ln_w = g.ln_w; ra.ln_b = g.ln_b; ra.Y = g.Y;
+  ra.X = g.X; ra.W = g.W; ra.Wt = g.Wt; ra.bias = g.bias; ra.res = g.res; ra.ln_w = g.ln_w; ra.ln_b = g.ln_b; ra.Y = g.Y;
   ra.N = g.N; ra.K = g.K; ra.act = g.act;
-  const int nsm = ring_ncta();
+  const int nsm = gemv_ring_ncta();
   {   // ring depth: what this CTA will stream, capped so the next kernel's CTA can co-reside (227 KB per SM)
     static int cap = 0;
     if (cap == 0) { const char* c = getenv("SV_RING_SLOTS"); cap = c ? atoi(c) : mega::STAGES; if (cap < 1 || cap > 6) cap = mega::STAGES; }

@@ -82,6 +82,7 @@ struct sv_engine {
   bool mega_debug = false;
   // dataflow persistent decode kernel (sv_decode_flow.cu): flagged exchange buffers in one allocation
   bool use_flow = false, flow_realloc = false;
+  bool use_tiles = false;           // slab-tiled weight copies exist: the ring GEMVs (and the dataflow kernel) stream those
   uint8_t* flow_mem = nullptr;
   size_t flow_bytes = 0;
   uint32_t *f_xa = nullptr, *f_xb = nullptr, *f_qkv = nullptr, *f_att = nullptr, *f_hb = nullptr;
@@ -480,9 +481,9 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
   RingGemvLaunch g{};
   g.B = B; g.ln_eps = d.ln_eps; g.n_head = d.n_head; g.n_kv = d.n_kv_head; g.tcap = e->tcap; g.state = e->state;
   g.amax_val = e->amax_val; g.amax_idx = e->amax_idx;
-  auto gemv = [&](const bf16* X, const bf16* W, const bf16* bias, const bf16* res, bf16* Y, int N, int K, int act,
+  auto gemv = [&](const bf16* X, const bf16* W, const uint8_t* Wt, const bf16* bias, const bf16* res, bf16* Y, int N, int K, int act,
                   const bf16* lw, const bf16* lb, int epi, bf16* kc, bf16* vc, bool p) {
-    g.X = X; g.W = W; g.bias = bias; g.res = res; g.Y = Y; g.N = N; g.K = K; g.act = act; g.ln_w = lw; g.ln_b = lb;
+    g.X = X; g.W = W; g.Wt = e->use_tiles ? Wt : nullptr; g.bias = bias; g.res = res; g.Y = Y; g.N = N; g.K = K; g.act = act; g.ln_w = lw; g.ln_b = lb;
     g.epi = epi; g.kcache = kc; g.vtcache = vc; g.pdl = p;
     launch_gemv_ring(g, st);
   };
@@ -490,7 +491,8 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
     const DecLayer& L = e->dec[i];
     bf16* kc = e->kcache + e->cache_layer_stride * i;
     bf16* vc = e->vtcache + e->cache_layer_stride * i;
-    gemv(e->d_x, L.attn_w, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, e->v2 ? 0 : 1, kc, vc,
+    const bool tl = e->use_tiles;
+    gemv(e->d_x, L.attn_w, tl ? e->t_attn[i] : nullptr, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, e->v2 ? 0 : 1, kc, vc,
          pdl && !first);
     first = false;
     if (e->v2)   // RoPE on q,k then append (the GEMV epilogue cannot rotate: the pair element lives in another tile)
@@ -498,17 +500,17 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
                          e->tcap, d.n_positions, pdl, st);
     launch_attention_decode_cluster(e->d_qkv, e->qkv_cols, kc, vc, e->d_attn, e->state, B, d.n_head, d.n_kv_head, D, e->tcap,
                                     std::min(ncta, 8), e->window, pdl, st);
-    gemv(e->d_attn, L.proj_w, L.proj_b, e->d_x, e->d_x, H, H, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
-    gemv(e->d_x, L.fc_w, L.fc_b, nullptr, e->d_h, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b, 0, nullptr, nullptr, pdl);
-    gemv(e->d_h, L.fc2_w, L.fc2_b, e->d_x, e->d_x, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
+    gemv(e->d_attn, L.proj_w, tl ? e->t_proj[i] : nullptr, L.proj_b, e->d_x, e->d_x, H, H, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
+    gemv(e->d_x, L.fc_w, tl ? e->t_fc[i] : nullptr, L.fc_b, nullptr, e->d_h, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b, 0, nullptr, nullptr, pdl);
+    gemv(e->d_h, L.fc2_w, tl ? e->t_fc2[i] : nullptr, L.fc2_b, e->d_x, e->d_x, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
   }
-  gemv(e->d_x, e->lm_head, nullptr, nullptr, e->logits, d.vocab, H, SV_ACT_NONE, e->lnf_w, e->lnf_b, 2, nullptr, nullptr, pdl);
+  gemv(e->d_x, e->lm_head, e->t_lm_src == e->lm_head ? e->t_lm_head : nullptr, nullptr, nullptr, e->logits, d.vocab, H, SV_ACT_NONE, e->lnf_w, e->lnf_b, 2, nullptr, nullptr, pdl);
   return SV_OK;
 }
 
 // (re)build the slab-tiled copies the dataflow kernel streams, after any weight changed
 void ensure_flow_tiles(sv_engine* e, cudaStream_t st) {
-  if (!e->use_flow || (!e->tiles_dirty && e->t_lm_src == e->lm_head)) return;
+  if (!e->use_tiles || (!e->tiles_dirty && e->t_lm_src == e->lm_head)) return;
   const sv_model_desc& d = e->d;
   const int nc = decode_flow_ncta();
   for (int i = 0; i < d.n_layer; ++i) {
@@ -566,10 +568,10 @@ static int finish_prefill_impl(sv_engine* e, int batch, int prefix_len, float* l
   hs.cur_len = e->prefix_len;
   for (int b = 0; b < batch; ++b) hs.unfinished[b] = 1;
   SV_CK(e, cudaMemcpyAsync(e->state, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));   // pageable: staged synchronously
+  ensure_flow_tiles(e, st);          // (no-op unless a weight changed since the last sequence)
   if (e->use_flow) {                 // new sequence: no word of the exchange buffers may carry a tag of the coming epochs
     SV_CK(e, cudaMemsetAsync(e->flow_mem, 0, e->flow_bytes, st));
     e->flow_epoch = 0;
-    ensure_flow_tiles(e, st);        // (no-op unless a weight changed since the last sequence)
   }
   if (last_logits) launch_logits_to_float(e->logits, last_logits, (int64_t)batch * e->d.vocab, st);
   SV_CK(e, cudaGetLastError());
@@ -673,9 +675,13 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
                         L.fc2_w, L.fc2_b, e->kcache + e->cache_layer_stride * i, e->vtcache + e->cache_layer_stride * i,
                         nullptr, nullptr, nullptr, nullptr};
     }
-    if (decode_flow_init() == cudaSuccess && decode_flow_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch, e->window, e->v2) &&
-        e->use_flow && e->fused_decode && d.n_layer <= 24) {
+    // slab-tiled copies of the decode weights (one bulk copy per ring slot instead of one per weight row: 7.1 vs 6.1 TB/s,
+    // profiles/r02_ring_stream.txt): streamed by the ring GEMVs of the graph path and by the dataflow kernel.  SV_TILED=0
+    // keeps the row-major weights only (saves one copy of the decoder in HBM).
+    const char* tl = getenv("SV_TILED");
+    if (decode_flow_init() == cudaSuccess && e->fused_decode && !(tl && !strcmp(tl, "0")) && decode_flow_ncta() == gemv_ring_ncta()) {
       const int nc = decode_flow_ncta();
+      e->use_tiles = true;
       bool ok = true;
       auto tiled = [&](int N, int K) -> uint8_t* {
         uint8_t* p = nullptr;
@@ -697,7 +703,7 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
       sv_engine_destroy(e);
       return fail(nullptr, SV_ERR_CUDA, "persistent decode kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    if (!decode_flow_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch, e->window, e->v2) || !e->fused_decode || d.n_layer > 24) e->use_flow = false;
+    if (!decode_flow_supported(d.hidden, d.n_inner, d.head_dim, d.max_batch, e->window, e->v2) || !e->fused_decode || d.n_layer > 24 || !e->use_tiles) e->use_flow = false;
     if (e->flow_realloc && !decode_flow_realloc_supported()) e->flow_realloc = false;
   }
   if (attention_decode_cluster_init() != cudaSuccess) {
@@ -1146,9 +1152,9 @@ int sv_debug_read_timeline(sv_engine* e, long long* out_host, int32_t n) {
 const char* sv_engine_describe(sv_engine* e) {
   if (!e) return "";
   char buf[512];
-  snprintf(buf, sizeof(buf), "decode=%s attn=cluster-dsmem pdl=%d linear_impl=%d flow[%s]",
+  snprintf(buf, sizeof(buf), "decode=%s weights=%s attn=cluster-dsmem pdl=%d linear_impl=%d flow[%s]",
            !e->fused_decode ? "legacy-kernels" : e->use_flow ? (e->flow_realloc ? "dataflow-kernel-setmaxnreg" : "dataflow-kernel") : "ring-gemv-graph",
-           (int)e->use_pdl, e->linear_impl, decode_flow_status());
+           e->use_tiles ? "slab-tiled" : "row-major", (int)e->use_pdl, e->linear_impl, decode_flow_status());
   e->describe = buf;
   return e->describe.c_str();
 }

@@ -110,6 +110,7 @@ struct MegaLayer {
 // one-phase weight-ring GEMV (same device code as the persistent kernel's GEMV phases)
 struct RingGemvLaunch {
   const bf16 *X, *W, *bias, *res, *ln_w, *ln_b;
+  const uint8_t* Wt;              // slab-tiled copy of W (flow_repack_kernel) or nullptr: then W's rows are copied one by one
   bf16* Y;
   int B, N, K, act, epi;          // epi: 0 plain, 1 QKV (+KV append), 2 lm_head (+argmax partials)
   float ln_eps;
@@ -123,6 +124,7 @@ struct RingGemvLaunch {
 cudaError_t gemv_ring_init();
 bool gemv_ring_supported(int K, bool has_ln);
 int gemv_ring_ntiles(int N);
+int gemv_ring_ncta();
 void launch_gemv_ring(const RingGemvLaunch& g, cudaStream_t st);
 // ---- sv_decode_flow.cu : dataflow persistent decode kernel (flagged activation words through L2, no grid barriers)
 struct FlowLaunch {

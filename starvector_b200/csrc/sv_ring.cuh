@@ -141,6 +141,24 @@ SV_DEVINL void produce_phase(Ring& r, const bf16* W, int N, int K, int cta, int 
   }
 }
 
+// ---- the same on the slab-tiled copy of W (flow_repack_kernel in sv_decode_flow.cu): a slab is SLOT_BYTES-aligned and already
+// has the shared-memory row pitch, so ONE bulk copy fills a slot (per-row 2 KB copies top out at ~6.1 TB/s, a 30 KB copy
+// reaches 7.1: profiles/r02_ring_stream.txt).  Rows past N are zero in the copy.
+SV_DEVINL void produce_phase_tiled(Ring& r, const uint8_t* T, int N, int K, int cta, int ncta, int lane) {
+  if (lane != 0) return;
+  const Plan p = make_plan(N, K, cta, ncta);
+  const uint8_t* src = T + (int64_t)cta * p.tpc * p.nstg * SLOT_BYTES;
+  const uint32_t bytes = (uint32_t)(p.R * p.pitch);
+  const int nslab = p.ntile * p.nstg;
+  for (int i = 0; i < nslab; ++i) {
+    const uint32_t fb = r.full0 + 8u * r.slot;
+    mbar_wait(r.empty0 + 8u * r.slot, r.phase ^ 1u);
+    mbar_expect_tx(fb, bytes);
+    bulk_g2s(r.base + r.slot * SLOT_BYTES, src + (int64_t)i * SLOT_BYTES, bytes, fb);
+    r.advance();
+  }
+}
+
 // ---- attention core on L2-only loads (same fragment walk as sv_attention.cu, see the comments there)
 SV_DEVINL void attn_block(const uint32_t (&qa)[D / 16][4], const bf16* __restrict__ kbase,
                           const bf16* __restrict__ vtbase, int tcap, int kb, int key_end, float scale_log2,
