@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SV_ABI_VERSION 3
+#define SV_ABI_VERSION 4
 #if defined(__GNUC__)
 #define SV_API __attribute__((visibility("default")))
 #else
@@ -102,6 +102,26 @@ typedef struct sv_gen_params {
   int32_t poll_interval;     /* host polls the device stop flag every this many steps (0 -> 16) */
 } sv_gen_params;
 
+/* Beam search / beam-sample parameters = what HF `generate(num_beams > 1)` receives from the reference
+ * (starvector_base.py:231-241: num_beams=2, do_sample, top_p, temperature, repetition_penalty, length_penalty;
+ * :289-295: early_stopping=True, pad_token_id; starvector_v2.py:53-57: nothing -> HF defaults). */
+typedef struct sv_beam_params {
+  int32_t num_beams;          /* >= 2; batch * num_beams <= 8 cache rows */
+  int32_t max_new_tokens;
+  int32_t do_sample;          /* 1 = beam-sample (candidates drawn without replacement, device Philox stream) */
+  int32_t early_stopping;     /* 0 = False (HF default), 1 = True (v1), 2 = "never" */
+  float temperature;
+  float top_p;
+  float repetition_penalty;   /* on the log-probs, over each running beam's own generated ids */
+  float length_penalty;
+  int32_t eos_token_id;       /* -1 = none */
+  int32_t pad_token_id;       /* fill of the returned rectangle (HF: pad if given, else eos) */
+  int32_t n_stop_ids;         /* 0..8: StoppingCriteriaSub, candidate 0 of image 0 matching ends every beam */
+  int32_t stop_ids[8];
+  int32_t poll_interval;      /* host polls the device done flag every this many steps (0 -> 16) */
+  uint64_t seed;
+} sv_beam_params;
+
 /* ---- lifecycle ------------------------------------------------------------------------ */
 SV_API int sv_abi_version(void);
 /* Replaces module construction (starvector_base.py:22-48): allocates packed weights, KV cache
@@ -146,6 +166,32 @@ SV_API int sv_reorder_cache(sv_engine* e, const int32_t* src_rows, void* stream)
  * logits and generation state are replicated, so the visual prefix is encoded and prefilled once per image, not once per
  * completion.  new_batch <= max_batch. */
 SV_API int sv_expand_batch(sv_engine* e, const int32_t* src_rows_host, int32_t new_batch, void* stream);
+/* `GenerationMixin._beam_search` after a prefill of batch * num_beams rows (every image repeated num_beams times,
+ * adjacent: HF `_expand_inputs_for_generation`): the whole search runs on the device -- per decode step the candidate
+ * selection, the beam bookkeeping and the cache permutation (as suffix copies between rows that diverged) follow the
+ * lm_head inside the replayed CUDA graph; the host only polls a done flag.  out_ids int32 [batch, max_new_tokens] = the best
+ * hypothesis per image (new tokens only, padded with pad_token_id), out_len int32 [batch] = rectangular length (HF's
+ * max_generated).  SV_ERR_UNSUPPORTED when a logits row does not fit the SM's shared memory (vocab > ~55k): use the
+ * host-stepped loop (sv_decode_step + sv_reorder_cache, starvector_b200/beam_search.py).  Synchronises `stream`. */
+SV_API int sv_beam_search(sv_engine* e, const sv_beam_params* p, int32_t batch, int32_t* out_ids, int32_t* out_len,
+                          void* stream);
+/* Host replays of the device stages of sv_beam_search (no GPU needed; the same bookkeeping code, sv_beam_core.h):
+ * parameter validation; size / initialisation / read-out of the opaque state blob; one logits row (fp32 values of the bf16
+ * logits) -> its 2 * num_beams best continuations {ordering key, log-prob + running score, token}; one bookkeeping step
+ * over row candidates [batch * num_beams][2 * num_beams] with the double-buffered sequence arrays
+ * [2][batch * num_beams][seq_stride] -> next tokens, parent rows (= HF beam_idx), returns 1 while the search continues.
+ * tests/test_beam_core.py runs whole searches with them against HF generate(num_beams > 1). */
+SV_API int sv_beam_params_check(const sv_beam_params* p, int32_t batch);
+SV_API int sv_beam_state_bytes(void);
+SV_API int sv_beam_state_init_host(const sv_beam_params* p, int32_t batch, int32_t first_cache_pos, void* state);
+SV_API int sv_beam_state_read_host(const void* state, int32_t* parity, int32_t* cur_len, int32_t* fin_len8,
+                                   float* beam_scores8);
+SV_API int sv_beam_row_candidates_host(const sv_beam_params* p, const float* logits, int32_t vocab, const int32_t* seq,
+                                       int32_t seq_len, float running_score, int32_t step, int32_t row, float* cand_key,
+                                       float* cand_val, int32_t* cand_tok);
+SV_API int sv_beam_step_host(const sv_beam_params* p, int32_t batch, int32_t vocab, int32_t seq_stride, void* state,
+                             const float* cand_key, const float* cand_val, const int32_t* cand_tok, int32_t* run_seq,
+                             int32_t* fin_seq, int32_t cache_hi, int32_t* next_tokens, int32_t* src_rows, int32_t* plan_out);
 /* GenerationMixin.generate() after the prefill (greedy / sampling loop, App. B): runs up to
  * max_new_tokens steps as a replayed CUDA graph.  out_ids int32 [B,max_new_tokens] (new tokens
  * only, padded with pad_token_id), out_len int32 [B] = rectangular generated length.

@@ -16,7 +16,7 @@ SV_OK, SV_ERR_INVALID, SV_ERR_CUDA, SV_ERR_UNSUPPORTED, SV_ERR_STATE = 0, -1, -2
 SV_DTYPE_BF16, SV_DTYPE_F32, SV_DTYPE_F16 = 0, 1, 2
 SV_ACT_NONE, SV_ACT_QUICKGELU, SV_ACT_GELU_TANH, SV_ACT_SILU = 0, 1, 2, 3
 SV_LINEAR_AUTO, SV_LINEAR_ROWGROUP, SV_LINEAR_TCGEN05 = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 SV_ALPHA_WHITE, SV_ALPHA_DROP = 0, 1
 
 
@@ -34,6 +34,15 @@ class GenParams(C.Structure):
         ("repetition_penalty", C.c_float), ("eos_token_id", C.c_int32), ("pad_token_id", C.c_int32),
         ("n_stop_ids", C.c_int32), ("stop_ids", C.c_int32 * 8), ("stop_row0_only", C.c_int32),
         ("seed", C.c_uint64), ("poll_interval", C.c_int32),
+    ]
+
+
+class BeamParams(C.Structure):
+    _fields_ = [
+        ("num_beams", C.c_int32), ("max_new_tokens", C.c_int32), ("do_sample", C.c_int32), ("early_stopping", C.c_int32),
+        ("temperature", C.c_float), ("top_p", C.c_float), ("repetition_penalty", C.c_float), ("length_penalty", C.c_float),
+        ("eos_token_id", C.c_int32), ("pad_token_id", C.c_int32), ("n_stop_ids", C.c_int32), ("stop_ids", C.c_int32 * 8),
+        ("poll_interval", C.c_int32), ("seed", C.c_uint64),
     ]
 
 
@@ -64,6 +73,15 @@ SIGNATURES = {
     "sv_decode_step": (C.c_int, [_P, _P, _P, _P]),
     "sv_reorder_cache": (C.c_int, [_P, _P, _P]),
     "sv_expand_batch": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "sv_beam_search": (C.c_int, [_P, C.POINTER(BeamParams), _I, _P, _P, _P]),
+    "sv_beam_params_check": (C.c_int, [C.POINTER(BeamParams), _I]),
+    "sv_beam_state_bytes": (C.c_int, []),
+    "sv_beam_state_init_host": (C.c_int, [C.POINTER(BeamParams), _I, _I, _P]),
+    "sv_beam_state_read_host": (C.c_int, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(C.c_float)]),
+    "sv_beam_row_candidates_host": (C.c_int, [C.POINTER(BeamParams), C.POINTER(C.c_float), _I, C.POINTER(_I), _I, _F, _I, _I,
+                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_I)]),
+    "sv_beam_step_host": (C.c_int, [C.POINTER(BeamParams), _I, _I, _I, _P, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                    C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "sv_generate": (C.c_int, [_P, C.POINTER(GenParams), _P, _P, _P]),
     "sv_generate_stream": (C.c_int, [_P, C.POINTER(GenParams), _P, _P, TOKEN_CALLBACK, _P, _P]),
     "sv_generate_im2svg_host": (C.c_int, [_P, _P, _I, _P, _I, C.POINTER(GenParams), _P, _P, _P]),

@@ -435,7 +435,7 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
       float acc = 0.f;
 #pragma unroll
       for (int w = 0; w < NWC; ++w) acc += rd[(w * 16 + en) * 8 + emm];
-      float v = 0.f;
+      float v = 0.f, v_bf = 0.f;          // v_bf: the value as the bf16 logits tensor holds it
       if (eok) {
         const float bv = bias_v;
         float rv = 0.f;
@@ -446,6 +446,7 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
         }
         v = epilogue_elem(acc, bv, act, res != nullptr, rv);
         const bf16 vb = __float2bfloat16_rn(v);
+        v_bf = __bfloat162float(vb);
         if (epi == EPI_LL) {
           st_rlx32(Y + emm * ll_words(N) + ll_off(ecol), EY | (uint32_t)__bfloat16_as_ushort(vb));
         } else {
@@ -457,7 +458,7 @@ SV_DEVINL void gemv_flow(FCtx& cx, Ring& r, LnRing& lr, const bool has_ln, const
         // (all 16 stores a partial covers come from this half-warp)
         if (cx.slow_select) { __threadfence(); __syncwarp(); }
         // greedy = argmax over the bf16 logits cast to float, lowest index wins ties (HF _sample)
-        float bv = eok ? v : -INFINITY;
+        float bv = eok ? v_bf : -INFINITY;
         int bi = eok ? ecol : 0x7fffffff;
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) {

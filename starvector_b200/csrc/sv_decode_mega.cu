@@ -277,12 +277,13 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
       for (int w = 0; w < NWC; ++w) acc += rd[(w * 16 + n) * 8 + mm];
       const int col = tile * p.R + n;
       const bool ok = n < p.R && col < N && mm < a.B;
-      float v = 0.f;
+      float v = 0.f, v_bf = 0.f;          // v_bf: the value as the bf16 logits tensor holds it
       if (ok) {
         const float bv = bias ? (cx.bias_s ? cx.bias_s[tl * 16 + n] : __bfloat162float(bias[col])) : 0.f;
         const float rv = res_pre;
         v = epilogue_elem(acc, bv, act, res != nullptr, rv);
         const bf16 vb = __float2bfloat16_rn(v);
+        v_bf = __bfloat162float(vb);
         Y[(int64_t)mm * N + col] = vb;
         if constexpr (EPI == EPI_QKV) {
           const int q_cols = a.n_head * D, j = col - q_cols;
@@ -299,7 +300,8 @@ SV_DEVINL void gemv_phase(const Ctx& cx, Ring& r, const bf16* __restrict__ X, co
         }
       }
       if constexpr (EPI == EPI_LMHEAD) {
-        float bv = ok ? v : -INFINITY;
+        // greedy = argmax over the bf16 logits cast to float, lowest index wins ties (HF _sample): reduce the ROUNDED value
+        float bv = ok ? v_bf : -INFINITY;
         int bi = ok ? col : 0x7fffffff;
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) {

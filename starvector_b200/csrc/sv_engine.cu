@@ -82,7 +82,8 @@ struct sv_engine {
   bool mega_debug = false;
   // dataflow persistent decode kernel (sv_decode_flow.cu): flagged exchange buffers in one allocation
   bool use_flow = false, flow_realloc = false;
-  bool use_tiles = false;           // slab-tiled weight copies exist: the ring GEMVs (and the dataflow kernel) stream those
+  bool use_tiles = false;           // slab-tiled weight copies exist (the dataflow kernel streams them)
+  bool ring_tiles = false;          // SV_TILED=1: the ring GEMVs of the graph path stream them too
   uint8_t* flow_mem = nullptr;
   size_t flow_bytes = 0;
   uint32_t *f_xa = nullptr, *f_xb = nullptr, *f_qkv = nullptr, *f_att = nullptr, *f_hb = nullptr;
@@ -95,6 +96,14 @@ struct sv_engine {
   bool tiles_dirty = true;
   int flow_epoch = 0;               // phase-tag epoch: steps run through the flow kernel since the buffers were cleared
   bf16 *kscratch = nullptr, *vscratch = nullptr;   // one layer of cache, for beam-search reorders
+  // device-resident beam search (sv_beam.cu), allocated by the first sv_beam_search call
+  svbeam::Params* beam_params = nullptr;
+  svbeam::State* beam_state = nullptr;
+  svbeam::Plan* beam_plan = nullptr;
+  float *beam_key = nullptr, *beam_val = nullptr;
+  int32_t *beam_tok = nullptr, *beam_run_seq = nullptr, *beam_fin_seq = nullptr;
+  bf16 *kstage = nullptr, *vstage = nullptr;        // staging copy of the cache for the KV suffix moves (all layers)
+  std::map<long long, GraphEntry> beam_graphs;
   bf16 *kcache, *vtcache;           // [layer][max_batch][n_kv][tcap][D] / [layer][max_batch][n_kv][D][tcap]
   int64_t cache_layer_stride = 0;
   GenState* state = nullptr;
@@ -483,7 +492,7 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
   g.amax_val = e->amax_val; g.amax_idx = e->amax_idx;
   auto gemv = [&](const bf16* X, const bf16* W, const uint8_t* Wt, const bf16* bias, const bf16* res, bf16* Y, int N, int K, int act,
                   const bf16* lw, const bf16* lb, int epi, bf16* kc, bf16* vc, bool p) {
-    g.X = X; g.W = W; g.Wt = e->use_tiles ? Wt : nullptr; g.bias = bias; g.res = res; g.Y = Y; g.N = N; g.K = K; g.act = act; g.ln_w = lw; g.ln_b = lb;
+    g.X = X; g.W = W; g.Wt = e->ring_tiles ? Wt : nullptr; g.bias = bias; g.res = res; g.Y = Y; g.N = N; g.K = K; g.act = act; g.ln_w = lw; g.ln_b = lb;
     g.epi = epi; g.kcache = kc; g.vtcache = vc; g.pdl = p;
     launch_gemv_ring(g, st);
   };
@@ -491,7 +500,7 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
     const DecLayer& L = e->dec[i];
     bf16* kc = e->kcache + e->cache_layer_stride * i;
     bf16* vc = e->vtcache + e->cache_layer_stride * i;
-    const bool tl = e->use_tiles;
+    const bool tl = e->ring_tiles;
     gemv(e->d_x, L.attn_w, tl ? e->t_attn[i] : nullptr, L.attn_b, nullptr, e->d_qkv, e->qkv_cols, H, SV_ACT_NONE, L.ln1_w, L.ln1_b, e->v2 ? 0 : 1, kc, vc,
          pdl && !first);
     first = false;
@@ -504,7 +513,7 @@ int run_decode_layers_fused(sv_engine* e, const int32_t* ids, int B, int ncta, b
     gemv(e->d_x, L.fc_w, tl ? e->t_fc[i] : nullptr, L.fc_b, nullptr, e->d_h, d.n_inner, H, SV_ACT_GELU_TANH, L.ln2_w, L.ln2_b, 0, nullptr, nullptr, pdl);
     gemv(e->d_h, L.fc2_w, tl ? e->t_fc2[i] : nullptr, L.fc2_b, e->d_x, e->d_x, H, d.n_inner, SV_ACT_NONE, nullptr, nullptr, 0, nullptr, nullptr, pdl);
   }
-  gemv(e->d_x, e->lm_head, e->t_lm_src == e->lm_head ? e->t_lm_head : nullptr, nullptr, nullptr, e->logits, d.vocab, H, SV_ACT_NONE, e->lnf_w, e->lnf_b, 2, nullptr, nullptr, pdl);
+  gemv(e->d_x, e->lm_head, (e->ring_tiles && e->t_lm_src == e->lm_head) ? e->t_lm_head : nullptr, nullptr, nullptr, e->logits, d.vocab, H, SV_ACT_NONE, e->lnf_w, e->lnf_b, 2, nullptr, nullptr, pdl);
   return SV_OK;
 }
 
@@ -675,13 +684,17 @@ int sv_engine_create(const sv_model_desc* desc, int device, sv_engine** out) {
                         L.fc2_w, L.fc2_b, e->kcache + e->cache_layer_stride * i, e->vtcache + e->cache_layer_stride * i,
                         nullptr, nullptr, nullptr, nullptr};
     }
-    // slab-tiled copies of the decode weights (one bulk copy per ring slot instead of one per weight row: 7.1 vs 6.1 TB/s,
-    // profiles/r02_ring_stream.txt): streamed by the ring GEMVs of the graph path and by the dataflow kernel.  SV_TILED=0
-    // keeps the row-major weights only (saves one copy of the decoder in HBM).
+    // slab-tiled copies of the decode weights (one bulk copy per ring slot instead of one per weight row): what the dataflow
+    // kernel streams (SV_FLOW=1), and optionally the ring GEMVs of the graph path (SV_TILED=1).  In the streaming
+    // microbenchmark one 30 KB copy per slot beats 16 row copies (7.1 vs 6.1 TB/s, profiles/r02_ring_stream.txt), but inside
+    // the decode step the row-major weights measured 2 % faster (0.932 vs 0.954 ms/token, profiles/r02_summary.md), so the
+    // default keeps ONE copy of the decoder in HBM.
     const char* tl = getenv("SV_TILED");
-    if (decode_flow_init() == cudaSuccess && e->fused_decode && !(tl && !strcmp(tl, "0")) && decode_flow_ncta() == gemv_ring_ncta()) {
+    const bool want_tiles = e->use_flow || (tl && !strcmp(tl, "1"));
+    if (want_tiles && decode_flow_init() == cudaSuccess && e->fused_decode && decode_flow_ncta() == gemv_ring_ncta()) {
       const int nc = decode_flow_ncta();
       e->use_tiles = true;
+      e->ring_tiles = tl && !strcmp(tl, "1");
       bool ok = true;
       auto tiled = [&](int N, int K) -> uint8_t* {
         uint8_t* p = nullptr;
@@ -725,6 +738,7 @@ void sv_engine_destroy(sv_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   for (auto& g : e->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  for (auto& g : e->beam_graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   for (void* p : e->allocs) cudaFree(p);
   if (e->host_flag) cudaFreeHost(e->host_flag);
   if (e->host_stream) cudaFreeHost(e->host_stream);
@@ -1095,6 +1109,138 @@ int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_t batch
   return r;
 }
 
+// Beam search with the whole loop on the device.  Graph body = one decode step over the batch * num_beams cache rows, then
+// candidates -> bookkeeping (+ next-token embeddings) -> KV suffix copies; the host replays it and polls `done`.
+int sv_beam_search(sv_engine* e, const sv_beam_params* bp, int32_t batch, int32_t* out_ids, int32_t* out_len, void* stream) {
+  if (!e || !bp || !out_ids) return fail(e, SV_ERR_INVALID, "null argument");
+  if (sv_beam_params_check(bp, batch) != SV_OK)
+    return fail(e, SV_ERR_INVALID, "bad beam parameters (need num_beams >= 2, batch * num_beams <= 8, max_new_tokens >= 1, "
+                                   "n_stop_ids in [0,8], early_stopping in {0,1,2}, temperature > 0, repetition_penalty > 0)");
+  if (!e->prefilled) return fail(e, SV_ERR_STATE, "sv_beam_search needs sv_prefill first");
+  if (e->host_cur_len != e->prefix_len) return fail(e, SV_ERR_STATE, "sv_beam_search must directly follow sv_prefill");
+  const sv_model_desc& d = e->d;
+  const int nb = bp->num_beams, R = batch * nb, max_new = bp->max_new_tokens, K = 2 * nb;
+  if (R != e->cur_batch) return fail(e, SV_ERR_STATE, "prefilled rows %d != batch %d x num_beams %d", e->cur_batch, batch, nb);
+  if (e->prefix_len + max_new > d.max_len)
+    return fail(e, SV_ERR_INVALID, "prefix %d + max_new_tokens %d exceeds max_len %d", e->prefix_len, max_new, d.max_len);
+  SV_CK(e, cudaSetDevice(e->device));
+  if (beam_init(d.vocab) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e, SV_ERR_UNSUPPORTED, "a logits row of %d entries does not fit the SM's shared memory: use the host-stepped beam loop", d.vocab);
+  }
+  LaunchScope scope(e);
+  const int stride = d.max_len;
+  if (!e->beam_state) {
+    bool ok = true;
+    const int MR = svbeam::kMaxRows, MK = svbeam::kMaxK;
+#define BAL(ptr, n) ok = ok && (dev_alloc(e, &e->ptr, (n)) == cudaSuccess)
+    BAL(beam_params, 1); BAL(beam_state, 1); BAL(beam_plan, 1);
+    BAL(beam_key, MR * MK); BAL(beam_val, MR * MK); BAL(beam_tok, MR * MK);
+    BAL(beam_run_seq, (int64_t)2 * MR * stride); BAL(beam_fin_seq, (int64_t)2 * MR * stride);
+    BAL(kstage, e->cache_layer_stride * d.n_layer); BAL(vstage, e->cache_layer_stride * d.n_layer);
+#undef BAL
+    if (!ok) { e->beam_state = nullptr; return fail(e, SV_ERR_CUDA, "allocation of the beam-search state failed: %s", cudaGetErrorString(cudaGetLastError())); }
+  }
+  cudaStream_t caller = (cudaStream_t)stream, st = e->gen_stream;
+  SV_CK(e, cudaEventRecord(e->ev_in, caller));
+  SV_CK(e, cudaStreamWaitEvent(st, e->ev_in, 0));
+
+  svbeam::Params hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.B = batch; hp.nb = nb; hp.K = K; hp.vocab = d.vocab; hp.max_length = max_new; hp.eos_id = bp->eos_token_id;
+  hp.n_stop = bp->n_stop_ids;
+  for (int i = 0; i < bp->n_stop_ids; ++i) hp.stop_ids[i] = bp->stop_ids[i];
+  hp.do_sample = bp->do_sample; hp.early_stopping = bp->early_stopping;
+  hp.min_keep = std::max(2, 1 + (bp->eos_token_id >= 0 ? 1 : 0));
+  hp.seq_stride = stride;
+  hp.temperature = bp->temperature; hp.top_p = bp->top_p; hp.rep_penalty = bp->repetition_penalty;
+  hp.length_penalty = bp->length_penalty; hp.seed = bp->seed;
+  svbeam::State hs;
+  memset(&hs, 0, sizeof(hs));
+  svbeam::init_state(hp, hs, e->prefix_len);
+  SV_CK(e, cudaMemcpyAsync(e->beam_params, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));   // pageable: staged synchronously
+  SV_CK(e, cudaMemcpyAsync(e->beam_state, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+  SV_CK(e, cudaMemsetAsync(e->beam_plan, 0, sizeof(svbeam::Plan), st));
+  launch_fill_i32(e->beam_run_seq, bp->pad_token_id, 2 * R * stride, st);
+  launch_fill_i32(e->beam_fin_seq, bp->pad_token_id, 2 * R * stride, st);
+
+  const bool fused = e->fused_decode;
+  auto bookkeeping = [&](int advance) {
+    launch_beam_candidates(e->logits, d.vocab, R, e->beam_params, e->beam_state, e->beam_run_seq, e->beam_key, e->beam_val,
+                           e->beam_tok, st);
+    launch_beam_step(e->beam_params, e->beam_state, e->beam_plan, e->beam_key, e->beam_val, e->beam_tok, e->beam_run_seq,
+                     e->beam_fin_seq, e->state, advance, bp->pad_token_id, e->wte, e->wpe, e->d_x, d.hidden, d.n_positions,
+                     e->next_ids, st);
+    launch_beam_kv_copy(e->kcache, e->vtcache, e->kstage, e->vstage, e->cache_layer_stride, d.n_layer, R, d.n_kv_head,
+                        e->tcap, d.head_dim, e->beam_plan, st);
+  };
+  bookkeeping(/*advance=*/0);                       // step 0: candidates from the prefill logits
+
+  const int nsplit = fused ? attention_decode_cluster_ncta(e->prefix_len + max_new) : nsplit_for(e, e->prefix_len + max_new);
+  const long long key = (long long)R * 100000 + nsplit * 8 + (fused ? 2 : 0) + (e->use_pdl ? 4 : 0);
+  GraphEntry& ge = e->beam_graphs[key];
+  if (!ge.exec && max_new > 1) {
+    for (int attempt = 0; attempt < 2 && !ge.exec; ++attempt) {
+      const bool pdl = e->use_pdl && fused && attempt == 0;
+      int64_t counted = 0;
+      g_launch_counter = &counted;
+      cudaGraph_t graph = nullptr;
+      SV_CK(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int r;
+      if (fused) r = run_decode_layers_fused(e, nullptr, R, nsplit, pdl, st);
+      else r = run_decode_layers(e, e->next_ids, R, nsplit, st);
+      bookkeeping(/*advance=*/1);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      g_launch_counter = &e->launches;
+      if (r != SV_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        ge.exec = nullptr;
+        cudaGetLastError();
+        if (!pdl) SV_CK(e, ce);
+        e->use_pdl = false;
+        continue;
+      }
+      ge.kernels = (int)counted;
+    }
+  }
+  const int poll = bp->poll_interval > 0 ? bp->poll_interval : 16;
+  SV_CK(e, cudaEventRecord(e->ev_t0, st));
+  int steps = 0;
+  bool done = false;
+  for (int s = 1; s < max_new && !done; ++s) {
+    SV_CK(e, cudaGraphLaunch(ge.exec, st));
+    e->launches += ge.kernels;
+    ++steps;
+    if (s % poll == 0) {
+      SV_CK(e, cudaMemcpyAsync(e->host_flag, &e->beam_state->done, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      SV_CK(e, cudaStreamSynchronize(st));
+      done = e->host_flag[0] != 0;
+    }
+  }
+  SV_CK(e, cudaEventRecord(e->ev_t1, st));
+  SV_CK(e, cudaMemcpyAsync(&hs, e->beam_state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  SV_CK(e, cudaStreamSynchronize(st));
+  SV_CK(e, cudaGetLastError());
+  if (!hs.done) return fail(e, SV_ERR_STATE, "beam search did not terminate within max_new_tokens steps (internal error)");
+  int n_gen = 0;
+  for (int b = 0; b < batch; ++b) n_gen = std::max(n_gen, hs.fin_len[b * nb]);     // HF: max_generated over the best beams
+  n_gen = std::min(n_gen, max_new);
+  launch_fill_i32(out_ids, bp->pad_token_id, batch * max_new, st);
+  // best hypothesis of image b = finished slot 0 = row b * nb of the live half of fin_seq
+  SV_CK(e, cudaMemcpy2DAsync(out_ids, (size_t)max_new * 4, e->beam_fin_seq + ((int64_t)hs.parity * R) * stride, (size_t)nb * stride * 4,
+                             (size_t)std::max(n_gen, 1) * 4, batch, cudaMemcpyDeviceToDevice, st));
+  if (out_len) launch_fill_i32(out_len, n_gen, batch, st);
+  SV_CK(e, cudaStreamSynchronize(st));
+  SV_CK(e, cudaGetLastError());
+  SV_CK(e, cudaEventElapsedTime(&e->last_decode_ms, e->ev_t0, e->ev_t1));
+  e->last_decode_steps = steps;
+  e->host_cur_len = e->prefix_len + hs.cur_len;
+  e->prefilled = false;
+  return SV_OK;
+}
+
 int sv_reorder_cache(sv_engine* e, const int32_t* src_rows, void* stream) {
   if (!e || !src_rows) return fail(e, SV_ERR_INVALID, "null argument");
   if (!e->prefilled) return fail(e, SV_ERR_STATE, "sv_reorder_cache needs a prefilled cache");
@@ -1154,7 +1300,7 @@ const char* sv_engine_describe(sv_engine* e) {
   char buf[512];
   snprintf(buf, sizeof(buf), "decode=%s weights=%s attn=cluster-dsmem pdl=%d linear_impl=%d flow[%s]",
            !e->fused_decode ? "legacy-kernels" : e->use_flow ? (e->flow_realloc ? "dataflow-kernel-setmaxnreg" : "dataflow-kernel") : "ring-gemv-graph",
-           e->use_tiles ? "slab-tiled" : "row-major", (int)e->use_pdl, e->linear_impl, decode_flow_status());
+           e->ring_tiles ? "slab-tiled" : "row-major", (int)e->use_pdl, e->linear_impl, decode_flow_status());
   e->describe = buf;
   return e->describe.c_str();
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "sv_beam_core.h"
 #include "sv_common.cuh"
 
 namespace sv {
@@ -158,5 +159,17 @@ bool decode_flow_realloc_supported();
 cudaError_t launch_decode_flow(const FlowLaunch& m, cudaStream_t st);
 size_t flow_tiled_bytes(int N, int K, int ncta);      // bytes of the slab-tiled copy of a [N][K] decode weight matrix
 void launch_flow_repack(const bf16* W, const bf16* bias, void* T, int N, int K, int ncta, cudaStream_t st);
+
+// ---- sv_beam.cu : beam search / beam-sample bookkeeping inside the decode graph (state structs: sv_beam_core.h)
+size_t beam_candidates_smem(int vocab);
+cudaError_t beam_init(int vocab);          // cudaErrorInvalidValue: a logits row does not fit the SM's shared memory
+void launch_beam_candidates(const bf16* logits, int vocab, int rows, const svbeam::Params* p, const svbeam::State* st,
+                            const int32_t* run_seq, float* cand_key, float* cand_val, int32_t* cand_tok, cudaStream_t st_);
+void launch_beam_step(const svbeam::Params* p, svbeam::State* st, svbeam::Plan* plan, const float* cand_key,
+                      const float* cand_val, const int32_t* cand_tok, int32_t* run_seq, int32_t* fin_seq, GenState* gs,
+                      int advance, int pad_fill, const bf16* wte, const bf16* wpe, bf16* x, int h, int n_positions,
+                      int32_t* next_ids, cudaStream_t st_);
+void launch_beam_kv_copy(bf16* kc, bf16* vc, bf16* kc2, bf16* vc2, int64_t layer_stride, int n_layer, int rows, int n_kv,
+                         int tcap, int D, const svbeam::Plan* plan, cudaStream_t st_);
 
 }  // namespace sv
