@@ -1,6 +1,13 @@
 """Beam search / beam-sample over the engine (the reference's default is `num_beams=2`,
 `do_sample=True`, `early_stopping=True` — starvector_base.py:231-234,292-295).
 
+Two implementations with one contract.  `impl="device"` (the default on a real engine): `sv_beam_search` -- candidate
+selection, the bookkeeping below (restated once more in csrc/sv_beam_core.h and pinned to HF by tests/test_beam_core.py) and
+the cache permutation all run inside the replayed decode graph; the host only polls a done flag.  `impl="host"`
+(`SV_BEAM=host`, or an engine without `beam_search_device`): the loop below, one `sv_decode_step` + `sv_reorder_cache` per
+step -- the torch restatement the device code is tested against, and the fallback for vocabularies that do not fit the
+candidate kernel's shared memory.
+
 The model forward of every step runs in the CUDA engine (beams are image rows: `sv_decode_step`, and the KV cache
 is permuted with `sv_reorder_cache`); the per-step bookkeeping below is a restatement of transformers'
 `GenerationMixin._beam_search` (generation/utils.py:2844-3425 in the installed 5.5.0: `_get_top_k_continuations`,
@@ -13,6 +20,7 @@ With `do_sample=False` the result is deterministic and is tested for equality wi
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -50,18 +58,35 @@ def _process_log_probs(log_probs: torch.Tensor, generated: torch.Tensor, repetit
 def beam_search(engine: Engine, image: Optional[torch.Tensor], prompt_ids: Optional[torch.Tensor], *, num_beams: int,
                 max_new_tokens: int, inputs_embeds: Optional[torch.Tensor] = None, do_sample: bool = False, temperature: float = 1.0, top_p: float = 1.0, repetition_penalty: float = 1.0,
                 length_penalty: float = 1.0, early_stopping=True, eos_token_id: Optional[int] = 0, pad_token_id: int = 0,
-                stop_ids: Sequence[int] = (), seed: int = 0) -> torch.Tensor:
+                stop_ids: Sequence[int] = (), seed: int = 0, impl: Optional[str] = None) -> torch.Tensor:
     """Returns int64 `[B, n_generated]`: the best finished (or running) beam per image, new tokens only."""
     src = inputs_embeds if inputs_embeds is not None else image
     B, nb = src.shape[0], int(num_beams)
     if B * nb > engine.dims.max_batch:
         raise ValueError(f"batch {B} x num_beams {nb} exceeds the engine's max_batch {engine.dims.max_batch}")
+    if impl is None:
+        impl = os.environ.get("SV_BEAM", "device")
+    if impl not in ("device", "host"):
+        raise ValueError("impl must be 'device' or 'host'")
+    on_device = impl == "device" and hasattr(engine, "beam_search_device")
     # _expand_inputs_for_generation: every image row becomes num_beams adjacent rows
     if inputs_embeds is not None:
-        logits = engine.prefill_embeds(inputs_embeds.repeat_interleave(nb, dim=0), return_logits=True)
+        logits = engine.prefill_embeds(inputs_embeds.repeat_interleave(nb, dim=0), return_logits=not on_device)
     else:
         engine.encode_images(image.repeat_interleave(nb, dim=0))
-        logits = engine.prefill(prompt_ids.repeat_interleave(nb, dim=0), return_logits=True)
+        logits = engine.prefill(prompt_ids.repeat_interleave(nb, dim=0), return_logits=not on_device)
+    if on_device:
+        fill_dev = (pad_token_id if pad_token_id is not None else eos_token_id) if eos_token_id is not None else -1
+        try:
+            return engine.beam_search_device(
+                B, num_beams=nb, max_new_tokens=max_new_tokens, do_sample=do_sample, temperature=temperature, top_p=top_p,
+                repetition_penalty=repetition_penalty, length_penalty=length_penalty, early_stopping=early_stopping,
+                eos_token_id=eos_token_id, pad_token_id=fill_dev, stop_ids=stop_ids, seed=seed).long()
+        except NotImplementedError:          # vocabulary too large for the candidate kernel: the host-stepped loop below
+            if inputs_embeds is not None:
+                logits = engine.prefill_embeds(inputs_embeds.repeat_interleave(nb, dim=0), return_logits=True)
+            else:
+                logits = engine.prefill(prompt_ids.repeat_interleave(nb, dim=0), return_logits=True)
     dev, V = logits.device, engine.dims.vocab
     max_length, cur_len, prompt_len = int(max_new_tokens), 0, 0          # generated-token coordinates (inputs_embeds)
     n_eos = 0 if eos_token_id is None else 1

@@ -206,6 +206,35 @@ class Engine:
         with self._lock:
             self._ck(self._lib.sv_reorder_cache(self._h, C.c_void_p(idx.data_ptr()), _stream_ptr(self.device)))
 
+    def beam_search_device(self, batch: int, *, num_beams: int, max_new_tokens: int, do_sample: bool = False,
+                           temperature: float = 1.0, top_p: float = 1.0, repetition_penalty: float = 1.0,
+                           length_penalty: float = 1.0, early_stopping=True, eos_token_id: Optional[int] = 0,
+                           pad_token_id: int = 0, stop_ids: Sequence[int] = (), seed: int = 0,
+                           poll_interval: int = 16) -> torch.Tensor:
+        """`sv_beam_search`: the whole beam search / beam-sample on the device, after a prefill of batch * num_beams rows
+        (every image repeated num_beams times, adjacent).  Returns int32 `[batch, n_generated]`, the best hypothesis per image.
+        Raises NotImplementedError when the vocabulary does not fit the candidate kernel (use the host-stepped loop)."""
+        if len(stop_ids) > 8:
+            raise ValueError("stop sequence longer than 8 tokens")
+        bp = _lib.BeamParams()
+        bp.num_beams, bp.max_new_tokens, bp.do_sample = int(num_beams), int(max_new_tokens), int(bool(do_sample))
+        bp.early_stopping = 2 if early_stopping == "never" else int(early_stopping is True)
+        bp.temperature, bp.top_p = float(temperature), float(top_p)
+        bp.repetition_penalty, bp.length_penalty = float(repetition_penalty), float(length_penalty)
+        bp.eos_token_id = -1 if eos_token_id is None else int(eos_token_id)
+        bp.pad_token_id = int(pad_token_id)
+        bp.n_stop_ids = len(stop_ids)
+        for i, t in enumerate(stop_ids):
+            bp.stop_ids[i] = int(t)
+        bp.poll_interval = int(poll_interval)
+        bp.seed = int(seed) & (2 ** 64 - 1)
+        out = torch.empty(batch, max(int(max_new_tokens), 1), dtype=torch.int32, device=self.device)
+        olen = torch.empty(batch, dtype=torch.int32, device=self.device)
+        with self._lock:
+            self._ck(self._lib.sv_beam_search(self._h, C.byref(bp), int(batch), C.c_void_p(out.data_ptr()),
+                                              C.c_void_p(olen.data_ptr()), _stream_ptr(self.device)))
+        return out[:, : int(olen[0].item())]
+
     def expand_batch(self, src_rows) -> None:
         """Prefix-KV sharing: right after a prefill, row r of the new batch becomes a copy of prefilled row src_rows[r]."""
         rows = [int(r) for r in src_rows]
