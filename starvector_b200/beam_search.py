@@ -35,6 +35,14 @@ def _gather_beams(t: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return torch.gather(t, 1, idx.expand(-1, -1, *t.shape[2:]))
 
 
+def _topk_stable(x: torch.Tensor, k: int):
+    """Top-k along the last dim with a DEFINED tie rule: equal values keep index order (lower flat index = lower beam, then
+    lower token id, first) -- the rule the device kernels follow (csrc/sv_beam_core.h).  bf16 logits tie often, and
+    torch.topk leaves the order of ties to the backend."""
+    v, i = torch.sort(x, dim=-1, descending=True, stable=True)
+    return v[..., :k], i[..., :k]
+
+
 def _process_log_probs(log_probs: torch.Tensor, generated: torch.Tensor, repetition_penalty: float, do_sample: bool,
                        temperature: float, top_p: float, min_keep: int) -> torch.Tensor:
     """logits_processor(flat_running_sequences, log_probs): repetition penalty -> temperature -> top-p (App. B.3)."""
@@ -117,7 +125,7 @@ def beam_search(engine: Engine, image: Optional[torch.Tensor], prompt_ids: Optio
             topk_indices = torch.multinomial(torch.softmax(log_probs, dim=-1), num_samples=K, generator=gen)
             topk_log_probs = torch.gather(log_probs, 1, topk_indices)
         else:
-            topk_log_probs, topk_indices = torch.topk(log_probs, k=K)
+            topk_log_probs, topk_indices = _topk_stable(log_probs, K)
         topk_beam = topk_indices // V
         topk_running_beam_indices = _gather_beams(running_beam_indices, topk_beam)
         topk_running_sequences = _gather_beams(running_sequences, topk_beam)
@@ -135,7 +143,7 @@ def beam_search(engine: Engine, image: Optional[torch.Tensor], prompt_ids: Optio
         hits = hits.view(B, K)
         # ---- _get_running_beams_for_next_iteration
         topk_running_log_probs = topk_log_probs + hits.to(torch.float32) * -1.0e9
-        next_idx = torch.topk(topk_running_log_probs, k=nb)[1]
+        next_idx = _topk_stable(topk_running_log_probs, nb)[1]
         running_sequences = _gather_beams(topk_running_sequences, next_idx)
         running_beam_scores = _gather_beams(topk_running_log_probs, next_idx)
         running_beam_indices = _gather_beams(topk_running_beam_indices, next_idx)
@@ -147,7 +155,7 @@ def beam_search(engine: Engine, image: Optional[torch.Tensor], prompt_ids: Optio
         fin_log_probs = fin_log_probs + (~unsatisfied).to(torch.float32) * -1.0e9
         fin_log_probs = fin_log_probs + (~just_finished) * -1.0e9
         merged_scores = torch.cat((beam_scores, fin_log_probs), dim=1)
-        top_merged = torch.topk(merged_scores, k=nb)[1]
+        top_merged = _topk_stable(merged_scores, nb)[1]
         sequences = _gather_beams(torch.cat((sequences, topk_running_sequences), dim=1), top_merged)
         beam_scores = _gather_beams(merged_scores, top_merged)
         beam_indices = _gather_beams(torch.cat((beam_indices, topk_running_beam_indices), dim=1), top_merged)
