@@ -28,7 +28,7 @@ def _oracle_fp32(d, sd):
     4.4 GB).  fp32, not bf16: hosts without AMX emulate bf16 matmuls ~20x slower, and the tolerances below are stated against
     fp32 anyway (the bf16 oracle itself is ~0.05 max / 0.01 mean away from it)."""
     if "o" not in _ORACLE:
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(min(32, os.cpu_count() or 1))   # as bench.py's CPU arm; with every logical CPU of the GPU box the 16-token B=8 oracle run took 250 s (8 s on 8 cores here)
         _ORACLE["o"] = OracleStarVector(d, sd, dtype=torch.float32, eos_token_id=None, pad_token_id=49152)
     return _ORACLE["o"]
 

@@ -184,7 +184,7 @@ def test_8b_dims_two_layers_vs_oracle():
     got = torch.stack(logits, dim=1).float().cpu()
     emb, vit = emb.float().cpu(), vit.float().cpu()
     eng.close()
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(min(32, os.cpu_count() or 1))   # as bench.py's CPU arm; with every logical CPU of the GPU box the 16-token B=8 oracle run took 250 s (8 s on 8 cores here)
     o = OracleStarVectorV2(d, sd, dtype=torch.float32)
     ref_vit = o.image_encoder(img.float())
     ref_emb = o.image_projection(ref_vit)
