@@ -127,20 +127,35 @@ def test_forward_scoring_matches_oracle(model):
 
 
 def test_grpo_shares_the_visual_prefix(model):
-    """num_return_sequences = G runs ONE encode + prefill per image (KV rows replicated), not G: fewer launches, same tokens."""
+    """num_return_sequences = G encodes and prefills every image ONCE (its KV rows are replicated by `sv_expand_batch`), never
+    the G-times expanded batch: the ViT and the prefill only ever see B rows, and each of the G greedy completions of an image
+    equals the single completion of a plain B-row call (same prefill batch, so bit-identical prefix; decode rows are
+    independent of each other)."""
     d, sd, m = model
     img = synthetic_images(d, 2, seed=1).cuda()
     P = len(m.model.svg_transformer.tokenizer("<svg")["input_ids"])
     kw = dict(use_nucleus_sampling=False, max_length=d.query_length + P + 6)
     eng = m.model.engine
-    n0 = eng.launch_count()
-    shared = m.model.generate_im2svg_grpo({"image": img}, num_return_sequences=2, **kw)["outputs"]
-    n_shared = eng.launch_count() - n0
-    n0 = eng.launch_count()
-    plain = m.model.generate_im2svg_ids({"image": img.repeat_interleave(2, dim=0)}, num_beams=1, **kw)
-    n_plain = eng.launch_count() - n0
-    assert torch.equal(shared.cpu(), plain.cpu())
-    assert n_shared < n_plain, (n_shared, n_plain)
+    calls = []
+    enc, pre = eng.encode_images, eng.prefill
+
+    def rec_encode(px, *a, **k):
+        calls.append(("encode", int(px.shape[0])))
+        return enc(px, *a, **k)
+
+    def rec_prefill(ids, *a, **k):
+        calls.append(("prefill", int(ids.shape[0])))
+        return pre(ids, *a, **k)
+
+    eng.encode_images, eng.prefill = rec_encode, rec_prefill
+    try:
+        shared = m.model.generate_im2svg_grpo({"image": img}, num_return_sequences=2, **kw)["outputs"].cpu()
+    finally:
+        del eng.encode_images, eng.prefill                      # drop the instance attributes: the class methods are back
+    assert ("prefill", 2) in calls and ("encode", 2) in calls and all(n == 2 for _, n in calls), calls
+    one = m.model.generate_im2svg_ids({"image": img}, num_beams=1, **kw).cpu()
+    assert shared.shape[0] == 4 and shared.shape[1] == one.shape[1], (shared.shape, one.shape)
+    assert torch.equal(shared[0::2], one) and torch.equal(shared[1::2], one), (shared.tolist(), one.tolist())
 
 
 def test_more_images_than_max_batch_runs_in_groups(model):
