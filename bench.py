@@ -329,6 +329,42 @@ def measure(model: str, B: int, n_new: int, steps: int, warmup: int, world: int,
     }
 
 
+def measure_beam(local: int, n_new: int = 512, num_beams: int = 2, passes: int = 2):
+    """The reference's DEFAULT generate() mode (starvector_base.py:231-241: num_beams=2; do_sample, top_p 0.9 when
+    use_nucleus_sampling) on this rank's GPU: 1 image x `num_beams` beams at StarVector-1B dims, the whole search on the device
+    (sv_beam_search).  EOS / stop disabled so that every pass runs `n_new` steps.  No collective: every rank runs it alone."""
+    from starvector_b200.beam_search import beam_search
+    from starvector_b200.config import dims_1b
+    from starvector_b200.engine import Engine
+    from starvector_b200.weights import synthetic_images, synthetic_state_dict
+
+    dev = torch.device("cuda", local)
+    d = dims_1b(max_batch=num_beams, max_len=257 + len(PROMPT_IDS) + n_new + 32)
+    eng = Engine(d, local)
+    eng.load_state_dict(synthetic_state_dict(d, seed=0))
+    img = synthetic_images(d, 1, seed=1).to(dev)
+    prompt = torch.tensor([PROMPT_IDS], dtype=torch.int32, device=dev)
+    out = {"workload": f"StarVector-1B dims, 1 image x {num_beams} beams, {n_new} steps, EOS/stop disabled, early_stopping='never'",
+           "loop": "device-resident (sv_beam_search): candidates, bookkeeping and KV suffix copies inside the replayed decode graph"}
+    for name, kw in (("beam_search", dict(do_sample=False)), ("beam_sample", dict(do_sample=True, top_p=0.9, temperature=1.0, seed=1234))):
+        def run():
+            return beam_search(eng, img, prompt, num_beams=num_beams, max_new_tokens=n_new, early_stopping="never", eos_token_id=None,
+                               pad_token_id=49152, impl="device", **kw)
+        run()
+        torch.cuda.synchronize(dev)
+        ms, toks, digs = [], [], []
+        for _ in range(passes):
+            ids = run()
+            m, st = eng.last_decode_timing()
+            ms.append(m / max(st, 1)); toks.append(int(ids.shape[1])); digs.append(ids_digest(ids))
+        step_ms = sum(ms) / len(ms)
+        out[name] = {"ms_per_beam_step": step_ms, "tokens_per_s": 1000.0 / step_ms, "tokens_returned": toks,
+                     "timing": "CUDA events around the replayed graph loop on the engine's stream, mean of %d passes" % passes,
+                     "identical_across_passes": len(set(digs)) == 1}
+    eng.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -410,6 +446,10 @@ def main():
             except Exception as e:                        # noqa: BLE001 - an extra must never cost the headline line
                 extras.append({"config": name, "error": f"{type(e).__name__}: {e}"[:300]})
         line["extra"] = {"configs": extras}
+        try:
+            line["extra"]["beam"] = measure_beam(local)
+        except Exception as e:                            # noqa: BLE001 - an extra must never cost the headline line
+            line["extra"]["beam"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == "1b" and not args.sampling:
         threads = min(os.cpu_count() or 1, CPU_THREADS_CAP)
