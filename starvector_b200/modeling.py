@@ -47,7 +47,8 @@ class _Transformer:
         params = self._hf_params(kw, prefix_len=inputs_embeds.shape[1])
         nb = int(kw.get("num_beams", 1))
         if nb > 1:
-            return o._beam_generate(params, kw, nb, inputs_embeds=inputs_embeds, early_stopping=bool(kw.get("early_stopping", False)))
+            es = kw.get("early_stopping", False)                                # HF: False (default) | True | "never"
+            return o._beam_generate(params, kw, nb, inputs_embeds=inputs_embeds, early_stopping=es if es == "never" else bool(es))
         o.engine.prefill_embeds(inputs_embeds)
         return o.engine.generate(params).long()
 
