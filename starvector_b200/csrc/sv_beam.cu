@@ -185,7 +185,10 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const Params* _
                                                                  const bf16* __restrict__ wte,
                                                                  const bf16* __restrict__ wpe, bf16* __restrict__ x, int h,
                                                                  int n_positions, int32_t* next_ids) {
-  if (st->done) return;
+  // every thread reads the flag BEFORE thread 0 can rewrite the state below (it may set done in this very step)
+  const int was_done = st->done;
+  __syncthreads();
+  if (was_done) return;
   __shared__ Plan plan;
   __shared__ int s_oldp, s_pos;
   __shared__ int s_finlen[svbeam::kMaxRows];
