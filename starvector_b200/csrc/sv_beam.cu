@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const Params* _
                                                                  const float* __restrict__ cand_key,
                                                                  const float* __restrict__ cand_val,
                                                                  const int32_t* __restrict__ cand_tok, int32_t* run_seq,
-                                                                 int32_t* fin_seq, GenState* gs, int advance, int pad_fill,
+                                                                 int32_t* fin_seq, GenState* gs, int advance,
                                                                  const bf16* __restrict__ wte,
                                                                  const bf16* __restrict__ wpe, bf16* __restrict__ x, int h,
                                                                  int n_positions, int32_t* next_ids) {
@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const Params* _
   __shared__ int s_finlen[svbeam::kMaxRows];
   const int tid = threadIdx.x;
   const int nb = pp->nb, K = pp->K, R = pp->B * nb, stride = pp->seq_stride;
+  const int pad_fill = pp->pad_id;          // (from the device-resident parameters: the captured graph serves every call)
   if (tid == 0) {
     const Params p = *pp;
     float mval[svbeam::kMaxRows * 2];
@@ -300,11 +301,11 @@ void launch_beam_candidates(const bf16* logits, int vocab, int rows, const Param
 }
 
 void launch_beam_step(const Params* p, State* st, Plan* plan, const float* cand_key, const float* cand_val,
-                      const int32_t* cand_tok, int32_t* run_seq, int32_t* fin_seq, GenState* gs, int advance, int pad_fill,
+                      const int32_t* cand_tok, int32_t* run_seq, int32_t* fin_seq, GenState* gs, int advance,
                       const bf16* wte, const bf16* wpe, bf16* x, int h, int n_positions, int32_t* next_ids,
                       cudaStream_t st_) {
   beam_step_kernel<<<1, kBeamThreads, 0, st_>>>(p, st, plan, cand_key, cand_val, cand_tok, run_seq, fin_seq, gs, advance,
-                                                pad_fill, wte, wpe, x, h, n_positions, next_ids);
+                                                wte, wpe, x, h, n_positions, next_ids);
   count_launch();
 }
 
@@ -327,6 +328,7 @@ static svbeam::Params params_from_abi(const sv_beam_params* bp, int32_t batch, i
   memset(&p, 0, sizeof(p));
   p.B = batch; p.nb = bp->num_beams; p.K = 2 * bp->num_beams; p.vocab = vocab; p.max_length = bp->max_new_tokens;
   p.eos_id = bp->eos_token_id;
+  p.pad_id = bp->pad_token_id;
   p.n_stop = bp->n_stop_ids;
   for (int i = 0; i < bp->n_stop_ids && i < svbeam::kMaxStop; ++i) p.stop_ids[i] = bp->stop_ids[i];
   p.do_sample = bp->do_sample; p.early_stopping = bp->early_stopping;

@@ -28,6 +28,7 @@ constexpr float kNegBig = -1.0e9f;
 struct Params {
   int32_t B, nb, K, vocab, max_length;      // max_length = max_new_tokens (generated coordinates)
   int32_t eos_id;                           // -1: none
+  int32_t pad_id;                           // fill of the sequence rectangles (HF: pad if given, else eos)
   int32_t n_stop, stop_ids[kMaxStop];       // StoppingCriteriaSub (row 0 of the flattened candidates ends everything)
   int32_t do_sample;
   int32_t early_stopping;                   // 0 False, 1 True, 2 "never"

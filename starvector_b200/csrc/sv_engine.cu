@@ -1148,6 +1148,7 @@ int sv_beam_search(sv_engine* e, const sv_beam_params* bp, int32_t batch, int32_
   svbeam::Params hp;
   memset(&hp, 0, sizeof(hp));
   hp.B = batch; hp.nb = nb; hp.K = K; hp.vocab = d.vocab; hp.max_length = max_new; hp.eos_id = bp->eos_token_id;
+  hp.pad_id = bp->pad_token_id;
   hp.n_stop = bp->n_stop_ids;
   for (int i = 0; i < bp->n_stop_ids; ++i) hp.stop_ids[i] = bp->stop_ids[i];
   hp.do_sample = bp->do_sample; hp.early_stopping = bp->early_stopping;
@@ -1169,8 +1170,7 @@ int sv_beam_search(sv_engine* e, const sv_beam_params* bp, int32_t batch, int32_
     launch_beam_candidates(e->logits, d.vocab, R, e->beam_params, e->beam_state, e->beam_run_seq, e->beam_key, e->beam_val,
                            e->beam_tok, st);
     launch_beam_step(e->beam_params, e->beam_state, e->beam_plan, e->beam_key, e->beam_val, e->beam_tok, e->beam_run_seq,
-                     e->beam_fin_seq, e->state, advance, bp->pad_token_id, e->wte, e->wpe, e->d_x, d.hidden, d.n_positions,
-                     e->next_ids, st);
+                     e->beam_fin_seq, e->state, advance, e->wte, e->wpe, e->d_x, d.hidden, d.n_positions, e->next_ids, st);
     launch_beam_kv_copy(e->kcache, e->vtcache, e->kstage, e->vstage, e->cache_layer_stride, d.n_layer, R, d.n_kv_head,
                         e->tcap, d.head_dim, e->beam_plan, st);
   };

@@ -167,7 +167,7 @@ void launch_beam_candidates(const bf16* logits, int vocab, int rows, const svbea
                             const int32_t* run_seq, float* cand_key, float* cand_val, int32_t* cand_tok, cudaStream_t st_);
 void launch_beam_step(const svbeam::Params* p, svbeam::State* st, svbeam::Plan* plan, const float* cand_key,
                       const float* cand_val, const int32_t* cand_tok, int32_t* run_seq, int32_t* fin_seq, GenState* gs,
-                      int advance, int pad_fill, const bf16* wte, const bf16* wpe, bf16* x, int h, int n_positions,
+                      int advance, const bf16* wte, const bf16* wpe, bf16* x, int h, int n_positions,
                       int32_t* next_ids, cudaStream_t st_);
 void launch_beam_kv_copy(bf16* kc, bf16* vc, bf16* kc2, bf16* vc2, int64_t layer_stride, int n_layer, int rows, int n_kv,
                          int tcap, int D, const svbeam::Plan* plan, cudaStream_t st_);
