@@ -207,3 +207,33 @@ def test_beam_sample_candidates_follow_the_distribution():
         counts[tok[0]] += 1
     tv = 0.5 * (counts / n - expect).abs().sum().item()
     assert tv < 0.04, tv
+
+
+class _QuantizedLogits(OracleBackedEngine):
+    """The oracle's logits rounded to multiples of 0.25: candidates tie at almost every step, as bf16 logits do at 49k vocab."""
+
+    def prefill(self, prompt_ids, return_logits=False):
+        return torch.round(super().prefill(prompt_ids, return_logits) * 4) / 4
+
+    def decode_step(self, ids):
+        return torch.round(super().decode_step(ids) * 4) / 4
+
+
+@pytest.mark.parametrize("nb,rp", [(2, 1.0), (3, 1.0), (4, 2.0)])
+def test_tie_rule_is_the_same_in_both_loops(setup, nb, rp):
+    """Equal scores are ordered by lower beam, then lower token id, in the device bookkeeping (sv_beam_core.h, argmax rounds with
+    removal + merge) and in the host-stepped loop (stable sort): with heavily tied logits the two must still return the same
+    hypotheses.  (HF itself leaves the order of ties to torch.topk, so this is pinned between our two implementations.)"""
+    d, o, img = setup
+    n_new = 12
+    kw = dict(num_beams=nb, max_new_tokens=n_new, repetition_penalty=rp, early_stopping=True, eos_token_id=0, pad_token_id=d.vocab - 4)
+    ids = torch.tensor([PROMPT] * 2)
+    ref = beam_search(_QuantizedLogits(o), img, ids, **kw)
+    # the quantised model really ties: count exact ties among the top candidates of the first step
+    q = _QuantizedLogits(o)
+    q.encode_images(img)
+    first = torch.log_softmax(q.prefill(ids, return_logits=True).float(), -1)
+    top = first.topk(8).values
+    assert int((top[:, 1:] == top[:, :-1]).sum()) >= 2, "no ties among the top-8 of the first step: the test lost its power"
+    got = core_beam_search(_QuantizedLogits(o), img, ids, **kw)
+    assert got.shape == ref.shape and torch.equal(got, ref), (got.tolist(), ref.tolist())
