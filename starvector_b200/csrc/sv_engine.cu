@@ -110,6 +110,8 @@ struct sv_engine {
   GenParamsDev* params = nullptr;
   uint8_t* seen = nullptr;
   int32_t *next_ids = nullptr, *out_ids = nullptr, *ids_tmp = nullptr;
+  bf16* im2svg_px = nullptr;        // staging of sv_generate_im2svg_host (pixels in, ids + lengths out): allocated by its first
+  int32_t* im2svg_out = nullptr;    //   call, sized for max_batch rows, kept for the engine's lifetime
   int32_t* host_flag = nullptr;     // pinned
   int32_t* host_stream = nullptr;   // pinned staging of streamed tokens [max_batch][kStreamChunk], allocated on first use
 
@@ -1083,15 +1085,19 @@ int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_t batch
   if (prompt_len < 1 || prompt_len > kMaxPrompt) return fail(e, SV_ERR_INVALID, "prompt_len outside [1,%d]", kMaxPrompt);
   SV_CK(e, cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->max_new_tokens < 1 || p->max_new_tokens > e->d.max_len)
+    return fail(e, SV_ERR_INVALID, "max_new_tokens %d outside [1,%d]", p->max_new_tokens, e->d.max_len);
   const size_t px_bytes = (size_t)batch * 3 * e->d.image_size * e->d.image_size * 2;
-  bf16* px = nullptr;
-  int32_t *dout = nullptr, *dlen = nullptr;
-  SV_CK(e, cudaMalloc(reinterpret_cast<void**>(&px), px_bytes));
-  cudaError_t ce = cudaMalloc(reinterpret_cast<void**>(&dout), ((size_t)batch * p->max_new_tokens + batch) * 4);
-  if (ce != cudaSuccess) { cudaFree(px); SV_CK(e, ce); }
-  dlen = dout + (size_t)batch * p->max_new_tokens;
+  // device staging of the host entry point: one allocation for the engine's lifetime (no cudaMalloc / cudaFree per call)
+  if (!e->im2svg_px && dev_alloc(e, &e->im2svg_px, (int64_t)e->d.max_batch * 3 * e->d.image_size * e->d.image_size) != cudaSuccess)
+    return fail(e, SV_ERR_CUDA, "allocation of the pixel staging buffer failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!e->im2svg_out && dev_alloc(e, &e->im2svg_out, (int64_t)e->d.max_batch * (e->d.max_len + 1)) != cudaSuccess)
+    return fail(e, SV_ERR_CUDA, "allocation of the output staging buffer failed: %s", cudaGetErrorString(cudaGetLastError()));
+  bf16* px = e->im2svg_px;
+  int32_t* dout = e->im2svg_out;
+  int32_t* dlen = dout + (size_t)batch * p->max_new_tokens;
   int r = SV_OK;
-  ce = cudaMemcpyAsync(px, pixels_host, px_bytes, cudaMemcpyHostToDevice, st);
+  cudaError_t ce = cudaMemcpyAsync(px, pixels_host, px_bytes, cudaMemcpyHostToDevice, st);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->ids_tmp, prompt_ids_host, (size_t)batch * prompt_len * 4, cudaMemcpyHostToDevice, st);
   if (ce != cudaSuccess) r = fail(e, SV_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(ce));
   if (r == SV_OK) r = sv_encode_images(e, px, batch, nullptr, nullptr, stream);
@@ -1104,8 +1110,6 @@ int sv_generate_im2svg_host(sv_engine* e, const void* pixels_host, int32_t batch
     if (ce != cudaSuccess) r = fail(e, SV_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(ce));
   }
   cudaStreamSynchronize(st);
-  cudaFree(px);
-  cudaFree(dout);
   return r;
 }
 
