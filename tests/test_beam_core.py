@@ -237,3 +237,54 @@ def test_tie_rule_is_the_same_in_both_loops(setup, nb, rp):
     assert int((top[:, 1:] == top[:, :-1]).sum()) >= 2, "no ties among the top-8 of the first step: the test lost its power"
     got = core_beam_search(_QuantizedLogits(o), img, ids, **kw)
     assert got.shape == ref.shape and torch.equal(got, ref), (got.tolist(), ref.tolist())
+
+
+class _SeededLogitsEngine:
+    """No model: the logits of a row are seeded noise of its token history (bf16-valued, full 1B vocabulary), so both loops see
+    identical logits for identical histories -- long searches at the real vocabulary size without a GPU."""
+
+    class _Dims:
+        pass
+
+    def __init__(self, vocab, num_beams, scale=2.0):
+        import hashlib
+
+        self._sha = hashlib.sha256
+        self.dims = self._Dims()
+        self.dims.vocab, self.dims.max_batch, self.dims.query_length = vocab, 8, 5
+        self.nb, self.scale, self.hist = num_beams, scale, None
+
+    def _logits(self):
+        rows = []
+        for h in self.hist:
+            seed = int.from_bytes(self._sha(repr(h).encode()).digest()[:7], "little")
+            g = torch.Generator().manual_seed(seed)
+            rows.append((torch.randn(self.dims.vocab, generator=g) * self.scale).to(torch.bfloat16).float())
+        return torch.stack(rows)
+
+    def encode_images(self, image):
+        pass
+
+    def prefill(self, prompt_ids, return_logits=False):
+        self.hist = [(("image", r // self.nb),) for r in range(prompt_ids.shape[0])]
+        return self._logits()
+
+    def decode_step(self, ids):
+        self.hist = [h + (int(t),) for h, t in zip(self.hist, ids.tolist())]
+        return self._logits()
+
+    def reorder_cache(self, idx):
+        self.hist = [self.hist[int(i)] for i in idx.tolist()]
+
+
+def test_long_search_at_the_1b_vocabulary_matches_the_host_loop():
+    """256 steps, 49,156-entry vocabulary, repetition_penalty 3.1, length_penalty -1, early_stopping "never" (the beam bench's
+    settings): running scores reach -10^3, every step reorders two beams that share a long prefix, the repetition-penalty set
+    grows to hundreds of tokens.  The host replays of the device stages must return the torch loop's hypothesis."""
+    V, n_new = 49156, 256
+    kw = dict(num_beams=2, max_new_tokens=n_new, repetition_penalty=3.1, length_penalty=-1.0, early_stopping="never",
+              eos_token_id=None, pad_token_id=49152)
+    img, ids = torch.zeros(1, 3, 4, 4), torch.tensor([[1, 2]])
+    ref = beam_search(_SeededLogitsEngine(V, 2), img, ids, **kw)
+    got = core_beam_search(_SeededLogitsEngine(V, 2), img, ids, **kw)
+    assert ref.shape == (1, n_new) and torch.equal(got, ref)
